@@ -1,0 +1,912 @@
+// C ABI of the engine (include/amuse_b200.h): context, weight staging / repacking, scheduler
+// tables, workspaces and the launch sequences of the sampler and the decoder.
+#include "../../include/amuse_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <unordered_map>
+#include <vector>
+
+#include "ast_kernels.cuh"
+#include "common.cuh"
+#include "decode_kernels.cuh"
+#include "denoise_loop.cuh"
+#include "small_kernels.cuh"
+
+using namespace amuse;
+
+namespace {
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+struct DevBuf {
+  float* p = nullptr;
+  size_t n = 0;   // floats
+  cudaError_t ensure(size_t want) {
+    if (want <= n) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(float));
+    if (e == cudaSuccess) n = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+struct Schedule {
+  int n_steps = 0;
+  std::vector<int32_t> timesteps;
+  std::vector<float> coef;   // [n][5]
+  int* d_timesteps = nullptr;
+  float* d_coef = nullptr;
+  float* d_temb = nullptr;
+  bool dir_uses_eps = true;
+  bool has_sigma = false;
+};
+
+const char* kBlocks[9] = {"input_blocks.0", "input_blocks.1", "input_blocks.2", "input_blocks.3", "middle_block",
+                          "output_blocks.0", "output_blocks.1", "output_blocks.2", "output_blocks.3"};
+
+// ---- decoder weights on the device (all K-major) ----------------------------------------
+struct DecLayerW {
+  size_t wqkv_t, bqkv, wo_t, bo, ln1, w1_t, b1, w2_t, b2, ln2, ln3;   // offsets (floats) into dec arena
+};
+struct DecW {
+  DevBuf arena;
+  DecLayerW L[9];
+  size_t skip_t[4], bskip[4];
+  size_t wv_t, bv, wco_t, bco;   // [9][128][128] / [9][128] cross-attention value + out projections
+  size_t norm, final_t, bfinal, pe;
+  bool ready = false;
+};
+
+struct DenW {
+  DevBuf blob, misc;
+  // offsets into misc
+  size_t freqs, w1t, b1, w2t, b2, condw[3], condb[3], pe, fnorm;
+  bool ready = false;
+};
+
+}  // namespace
+
+struct amuse_ctx {
+  int device = 0;
+  std::string err;
+  std::unordered_map<std::string, HostTensor> raw;
+  std::vector<float> alphas_cumprod;   // 1000 entries; default computed at create
+  DenW den;
+  DecW dec;
+  ast::Weights astw;
+  std::map<std::tuple<int, int, int>, Schedule> schedules;   // (sampler, n_steps, eta bits)
+  // workspaces
+  DevBuf cond, lat_tmp, lat_out, one_coef;
+  DevBuf dXA, dXB, dXC, dQKV, dO, dH, dSkip, dFeats, dCvec, dZero;
+  DevBuf h2d;   // staging for the *_host entry point
+  long long* d_prof = nullptr;
+  int prof_step = -1;
+  int64_t launches = 0;
+  int dec_chunk = 32;   // clips per decoder pass (keeps the working set inside the 126 MB L2)
+};
+
+namespace {
+
+int fail(amuse_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) return fail(ctx, AMUSE_E_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+const HostTensor* find(amuse_ctx* c, const std::string& k) {
+  auto it = c->raw.find(k);
+  return it == c->raw.end() ? nullptr : &it->second;
+}
+
+// Default alphas_cumprod: scaled_linear betas (configs/diff_latent_v2.json:57-66) evaluated in
+// double and rounded once to fp32.  torch's own fp32 linspace differs from this in the last bit
+// of some entries (its vectorised kernel is build/CPU dependent), so the Python host passes the
+// table torch produces on the host machine via "scheduler.alphas_cumprod" for exact parity.
+void default_alphas(std::vector<float>& ac) {
+  const int n = 1000;
+  const double s = std::sqrt(0.00085), e = std::sqrt(0.012);
+  ac.resize(n);
+  double prod = 1.0;
+  for (int i = 0; i < n; ++i) {
+    const float b = static_cast<float>(s + (e - s) * i / (n - 1));
+    const float beta = b * b;
+    const float alpha = 1.0f - beta;
+    prod *= static_cast<double>(alpha);   // torch CPU cumprod accumulates fp32 inputs in double
+    ac[i] = static_cast<float>(prod);
+  }
+}
+
+// Scheduler scalars in fp32, in the operation order of diffusers 0.17.1 `step()` (restated,
+// SURVEY.md App. B.1 / B.2; oracle twin: oracle/lpdm_ref.py ddim_coeffs / ddpm_coeffs).
+int build_schedule(amuse_ctx* ctx, int n_steps, int sampler, float eta, Schedule& sc) {
+  const std::vector<float>& ac = ctx->alphas_cumprod;
+  const int N = static_cast<int>(ac.size());
+  if (n_steps < 1 || n_steps > N) return fail(ctx, AMUSE_E_INVALID, "n_steps %d out of range", n_steps);
+  const int r = N / n_steps;
+  sc.n_steps = n_steps;
+  sc.timesteps.resize(n_steps);
+  sc.coef.assign(static_cast<size_t>(n_steps) * 5, 0.f);
+  sc.has_sigma = false;
+  if (sampler == AMUSE_SAMPLER_DDIM) {
+    sc.dir_uses_eps = true;
+    for (int i = 0; i < n_steps; ++i) {
+      const int t = (n_steps - 1 - i) * r + 1;   // steps_offset = 1 ("leading" spacing)
+      if (t >= N)
+        return fail(ctx, AMUSE_E_INVALID,
+                    "DDIM with %d steps indexes alphas_cumprod[%d] (steps_offset=1): invalid in the reference too", n_steps, t);
+      sc.timesteps[i] = t;
+      const int p = t - r;
+      const float a = ac[t], ap = (p >= 0) ? ac[p] : ac[0];   // set_alpha_to_one = False
+      const float bp = 1.0f - a, bpp = 1.0f - ap;
+      const float var = (bpp / bp) * (1.0f - a / ap);
+      const float sd = eta * std::sqrt(var);
+      float* c = &sc.coef[static_cast<size_t>(i) * 5];
+      c[0] = std::sqrt(a);
+      c[1] = std::sqrt(bp);
+      c[2] = std::sqrt(ap);
+      c[3] = std::sqrt(1.0f - ap - sd * sd);
+      c[4] = sd;
+      if (sd != 0.f) sc.has_sigma = true;
+    }
+  } else if (sampler == AMUSE_SAMPLER_DDPM) {
+    sc.dir_uses_eps = false;
+    for (int i = 0; i < n_steps; ++i) {
+      const int t = (n_steps - 1 - i) * r;
+      sc.timesteps[i] = t;
+      const int p = t - r;
+      const float a = ac[t], ap = (p >= 0) ? ac[p] : 1.0f;
+      const float bp = 1.0f - a, bpp = 1.0f - ap;
+      const float alpha_t = a / ap, beta_t = 1.0f - alpha_t;
+      float* c = &sc.coef[static_cast<size_t>(i) * 5];
+      c[0] = std::sqrt(a);
+      c[1] = std::sqrt(bp);
+      c[2] = (std::sqrt(ap) * beta_t) / bp;
+      c[3] = std::sqrt(alpha_t) * bpp / bp;
+      float var = (1.0f - ap) / (1.0f - a) * beta_t;   // fixed_small
+      if (var < 1e-20f) var = 1e-20f;
+      c[4] = (t > 0) ? std::sqrt(var) : 0.f;
+      if (c[4] != 0.f) sc.has_sigma = true;
+    }
+  } else {
+    return fail(ctx, AMUSE_E_INVALID, "unknown sampler %d", sampler);
+  }
+  return AMUSE_OK;
+}
+
+int get_schedule(amuse_ctx* ctx, int n_steps, int sampler, float eta, cudaStream_t st, Schedule** out) {
+  uint32_t eb;
+  std::memcpy(&eb, &eta, 4);
+  auto key = std::make_tuple(sampler, n_steps, static_cast<int>(eb));
+  auto it = ctx->schedules.find(key);
+  if (it != ctx->schedules.end()) {
+    *out = &it->second;
+    return AMUSE_OK;
+  }
+  Schedule sc;
+  int rc = build_schedule(ctx, n_steps, sampler, eta, sc);
+  if (rc) return rc;
+  CU(cudaMalloc(&sc.d_timesteps, sizeof(int) * n_steps));
+  CU(cudaMalloc(&sc.d_coef, sizeof(float) * 5 * n_steps));
+  CU(cudaMalloc(&sc.d_temb, sizeof(float) * 128 * n_steps));
+  CU(cudaMemcpyAsync(sc.d_timesteps, sc.timesteps.data(), sizeof(int) * n_steps, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(sc.d_coef, sc.coef.data(), sizeof(float) * 5 * n_steps, cudaMemcpyHostToDevice, st));
+  // a3: the time tokens of every step, once per schedule (batch-invariant)
+  const float* m = ctx->den.misc.p;
+  CU(launch_time_table(sc.d_timesteps, n_steps, m + ctx->den.freqs, m + ctx->den.w1t, m + ctx->den.b1,
+                       m + ctx->den.w2t, m + ctx->den.b2, sc.d_temb, st));
+  ctx->launches++;
+  CU(cudaStreamSynchronize(st));   // host vectors above must outlive the async copies
+  auto ins = ctx->schedules.emplace(key, std::move(sc));
+  *out = &ins.first->second;
+  return AMUSE_OK;
+}
+
+void drop_schedules(amuse_ctx* ctx) {
+  for (auto& kv : ctx->schedules) {
+    cudaFree(kv.second.d_timesteps);
+    cudaFree(kv.second.d_coef);
+    cudaFree(kv.second.d_temb);
+  }
+  ctx->schedules.clear();
+}
+
+// -------------------------------------------------------------------- denoiser packing
+int need(amuse_ctx* ctx, const std::string& k, std::initializer_list<int64_t> shape, const HostTensor** out) {
+  const HostTensor* t = find(ctx, k);
+  if (!t) return fail(ctx, AMUSE_E_MISSING, "weight '%s' was not loaded", k.c_str());
+  std::vector<int64_t> want(shape);
+  if (t->shape != want) return fail(ctx, AMUSE_E_INVALID, "weight '%s' has the wrong shape", k.c_str());
+  *out = t;
+  return AMUSE_OK;
+}
+#define NEED(var, key, ...)                                  \
+  const HostTensor* var = nullptr;                           \
+  if (int rc__ = need(ctx, key, {__VA_ARGS__}, &var)) return rc__;
+
+void transpose_into(float* dst, const float* src, int rows, int cols) {   // src [rows][cols] -> dst [cols][rows]
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < cols; ++c) dst[static_cast<size_t>(c) * rows + r] = src[static_cast<size_t>(r) * cols + c];
+}
+
+int pack_denoiser(amuse_ctx* ctx, cudaStream_t st) {
+  using namespace dn;
+  const std::string P = "denoiser.";
+  std::vector<float> blob(static_cast<size_t>(kCluster) * kBlobRankFloats, 0.f);
+  for (int l = 0; l < 9; ++l) {
+    const std::string b = P + "encoder." + kBlocks[l];
+    NEED(inw, b + ".self_attn.in_proj_weight", 384, 128);
+    NEED(inb, b + ".self_attn.in_proj_bias", 384);
+    NEED(ow, b + ".self_attn.out_proj.weight", 128, 128);
+    NEED(ob, b + ".self_attn.out_proj.bias", 128);
+    NEED(w1, b + ".linear1.weight", 512, 128);
+    NEED(b1, b + ".linear1.bias", 512);
+    NEED(w2, b + ".linear2.weight", 128, 512);
+    NEED(b2, b + ".linear2.bias", 128);
+    NEED(n1w, b + ".norm1.weight", 128);
+    NEED(n1b, b + ".norm1.bias", 128);
+    NEED(n2w, b + ".norm2.weight", 128);
+    NEED(n2b, b + ".norm2.bias", 128);
+    const HostTensor *skw = nullptr, *skb = nullptr;
+    if (l >= 5) {
+      const std::string s = P + "encoder.linear_blocks." + std::to_string(l - 5);
+      if (int rc = need(ctx, s + ".weight", {128, 256}, &skw)) return rc;
+      if (int rc = need(ctx, s + ".bias", {128}, &skb)) return rc;
+    }
+    for (int rank = 0; rank < kCluster; ++rank) {
+      float* base = blob.data() + static_cast<size_t>(rank) * kBlobRankFloats;
+      const int head = rank >> 1;
+      int off, n;
+      const int t0 = (l < 5) ? 4 * l : 20 + 5 * (l - 5) + 1;   // index of this layer's QKV tile
+      if (l >= 5) {   // skip tile: Wt[k][c] = W[16*rank + c][k]
+        tile_info(t0 - 1, off, n);
+        float* t = base + off;
+        for (int k = 0; k < 256; ++k)
+          for (int c = 0; c < 16; ++c) t[k * 16 + c] = skw->data[static_cast<size_t>(rank * 16 + c) * 256 + k];
+        for (int c = 0; c < 16; ++c) t[256 * 16 + c] = skb->data[rank * 16 + c];
+      }
+      {   // QKV tile of head `head`: local col j -> in_proj row  (j/32)*128 + head*32 + j%32
+        tile_info(t0, off, n);
+        float* t = base + off;
+        for (int j = 0; j < 96; ++j) {
+          const int row = (j / 32) * 128 + head * 32 + (j % 32);
+          for (int k = 0; k < 128; ++k) t[k * 96 + j] = inw->data[static_cast<size_t>(row) * 128 + k];
+          t[128 * 96 + j] = inb->data[row];
+        }
+      }
+      {   // out_proj columns of the head: Wt[kk][n] = Wo[n][head*32 + kk]; + bo + norm1
+        tile_info(t0 + 1, off, n);
+        float* t = base + off;
+        for (int kk = 0; kk < 32; ++kk)
+          for (int c = 0; c < 128; ++c) t[kk * 128 + c] = ow->data[static_cast<size_t>(c) * 128 + head * 32 + kk];
+        std::memcpy(t + 32 * 128, ob->data.data(), 128 * 4);
+        std::memcpy(t + 32 * 128 + 128, n1w->data.data(), 128 * 4);
+        std::memcpy(t + 32 * 128 + 256, n1b->data.data(), 128 * 4);
+      }
+      {   // linear1 rows [64*rank, +64): Wt[k][j]
+        tile_info(t0 + 2, off, n);
+        float* t = base + off;
+        for (int j = 0; j < 64; ++j) {
+          for (int k = 0; k < 128; ++k) t[k * 64 + j] = w1->data[static_cast<size_t>(rank * 64 + j) * 128 + k];
+          t[128 * 64 + j] = b1->data[rank * 64 + j];
+        }
+      }
+      {   // linear2 columns [64*rank, +64): Wt[kk][n] = W2[n][64*rank + kk]; + b2 + norm2
+        tile_info(t0 + 3, off, n);
+        float* t = base + off;
+        for (int kk = 0; kk < 64; ++kk)
+          for (int c = 0; c < 128; ++c) t[kk * 128 + c] = w2->data[static_cast<size_t>(c) * 512 + rank * 64 + kk];
+        std::memcpy(t + 64 * 128, b2->data.data(), 128 * 4);
+        std::memcpy(t + 64 * 128 + 128, n2w->data.data(), 128 * 4);
+        std::memcpy(t + 64 * 128 + 256, n2b->data.data(), 128 * 4);
+      }
+    }
+  }
+  // misc: time embedding (K-major), condition projections (K-major), PE, final norm, freqs
+  NEED(tw1, P + "time_embedding.linear_1.weight", 128, 256);
+  NEED(tb1, P + "time_embedding.linear_1.bias", 128);
+  NEED(tw2, P + "time_embedding.linear_2.weight", 128, 128);
+  NEED(tb2, P + "time_embedding.linear_2.bias", 128);
+  NEED(pe, P + "query_pos.pe", 500, 1, 128);
+  NEED(fnw, P + "encoder.norm.weight", 128);
+  NEED(fnb, P + "encoder.norm.bias", 128);
+  std::vector<float> misc;
+  auto put = [&](size_t n) {
+    size_t o = misc.size();
+    misc.resize(o + ((n + 3) & ~size_t(3)), 0.f);
+    return o;
+  };
+  DenW& d = ctx->den;
+  d.freqs = put(128);
+  if (const HostTensor* f = find(ctx, P + "time_proj.freqs")) {
+    if (f->numel() != 128) return fail(ctx, AMUSE_E_INVALID, "denoiser.time_proj.freqs must have 128 entries");
+    std::memcpy(&misc[d.freqs], f->data.data(), 128 * 4);
+  } else {
+    for (int i = 0; i < 128; ++i)   // exp(-ln(10000) * i / 128), embeddings.py:264-270 (freq_shift 0)
+      misc[d.freqs + i] = static_cast<float>(std::exp(static_cast<double>(static_cast<float>(-std::log(10000.0)) *
+                                                                         static_cast<float>(i) / 128.0f)));
+  }
+  d.w1t = put(256 * 128);
+  transpose_into(&misc[d.w1t], tw1->data.data(), 128, 256);
+  d.b1 = put(128);
+  std::memcpy(&misc[d.b1], tb1->data.data(), 128 * 4);
+  d.w2t = put(128 * 128);
+  transpose_into(&misc[d.w2t], tw2->data.data(), 128, 128);
+  d.b2 = put(128);
+  std::memcpy(&misc[d.b2], tb2->data.data(), 128 * 4);
+  const char* cn[3] = {"con", "emo", "sty"};
+  for (int i = 0; i < 3; ++i) {
+    NEED(cw, P + "emb_proj_" + cn[i] + ".1.weight", 128, 256);
+    NEED(cb, P + "emb_proj_" + cn[i] + ".1.bias", 128);
+    d.condw[i] = put(256 * 128);
+    transpose_into(&misc[d.condw[i]], cw->data.data(), 128, 256);
+    d.condb[i] = put(128);
+    std::memcpy(&misc[d.condb[i]], cb->data.data(), 128 * 4);
+  }
+  d.pe = put(500 * 128);
+  std::memcpy(&misc[d.pe], pe->data.data(), 500 * 128 * 4);
+  d.fnorm = put(256);
+  std::memcpy(&misc[d.fnorm], fnw->data.data(), 128 * 4);
+  std::memcpy(&misc[d.fnorm + 128], fnb->data.data(), 128 * 4);
+
+  CU(d.blob.ensure(blob.size()));
+  CU(d.misc.ensure(misc.size()));
+  CU(cudaMemcpyAsync(d.blob.p, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d.misc.p, misc.data(), misc.size() * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  d.ready = true;
+  drop_schedules(ctx);   // time tables depend on the weights
+  return AMUSE_OK;
+}
+
+// -------------------------------------------------------------------- decoder packing
+int pack_decoder(amuse_ctx* ctx, cudaStream_t st) {
+  const std::string P = "vae.";
+  std::vector<float> ar;
+  auto put = [&](size_t n) {
+    size_t o = ar.size();
+    ar.resize(o + ((n + 3) & ~size_t(3)), 0.f);
+    return o;
+  };
+  DecW& d = ctx->dec;
+  d.wv_t = put(9 * 128 * 128);
+  d.bv = put(9 * 128);
+  d.wco_t = put(9 * 128 * 128);
+  d.bco = put(9 * 128);
+  for (int l = 0; l < 9; ++l) {
+    const std::string b = P + "decoder." + kBlocks[l];
+    NEED(inw, b + ".self_attn.in_proj_weight", 384, 128);
+    NEED(inb, b + ".self_attn.in_proj_bias", 384);
+    NEED(ow, b + ".self_attn.out_proj.weight", 128, 128);
+    NEED(ob, b + ".self_attn.out_proj.bias", 128);
+    NEED(cw, b + ".multihead_attn.in_proj_weight", 384, 128);
+    NEED(cb, b + ".multihead_attn.in_proj_bias", 384);
+    NEED(cow, b + ".multihead_attn.out_proj.weight", 128, 128);
+    NEED(cob, b + ".multihead_attn.out_proj.bias", 128);
+    NEED(w1, b + ".linear1.weight", 512, 128);
+    NEED(b1, b + ".linear1.bias", 512);
+    NEED(w2, b + ".linear2.weight", 128, 512);
+    NEED(b2, b + ".linear2.bias", 128);
+    DecLayerW& L = d.L[l];
+    L.wqkv_t = put(128 * 384);
+    transpose_into(&ar[L.wqkv_t], inw->data.data(), 384, 128);
+    L.bqkv = put(384);
+    std::memcpy(&ar[L.bqkv], inb->data.data(), 384 * 4);
+    L.wo_t = put(128 * 128);
+    transpose_into(&ar[L.wo_t], ow->data.data(), 128, 128);
+    L.bo = put(128);
+    std::memcpy(&ar[L.bo], ob->data.data(), 128 * 4);
+    L.w1_t = put(128 * 512);
+    transpose_into(&ar[L.w1_t], w1->data.data(), 512, 128);
+    L.b1 = put(512);
+    std::memcpy(&ar[L.b1], b1->data.data(), 512 * 4);
+    L.w2_t = put(512 * 128);
+    transpose_into(&ar[L.w2_t], w2->data.data(), 128, 512);
+    L.b2 = put(128);
+    std::memcpy(&ar[L.b2], b2->data.data(), 128 * 4);
+    size_t* lns[3] = {&L.ln1, &L.ln2, &L.ln3};
+    for (int q = 0; q < 3; ++q) {
+      NEED(nw, b + ".norm" + std::to_string(q + 1) + ".weight", 128);
+      NEED(nb, b + ".norm" + std::to_string(q + 1) + ".bias", 128);
+      *lns[q] = put(256);
+      std::memcpy(&ar[*lns[q]], nw->data.data(), 128 * 4);
+      std::memcpy(&ar[*lns[q] + 128], nb->data.data(), 128 * 4);
+    }
+    // cross attention over a 1-token memory: only W_v (rows 256..383) and out_proj matter
+    transpose_into(&ar[d.wv_t + static_cast<size_t>(l) * 128 * 128], cw->data.data() + 256 * 128, 128, 128);
+    std::memcpy(&ar[d.bv + l * 128], cb->data.data() + 256, 128 * 4);
+    transpose_into(&ar[d.wco_t + static_cast<size_t>(l) * 128 * 128], cow->data.data(), 128, 128);
+    std::memcpy(&ar[d.bco + l * 128], cob->data.data(), 128 * 4);
+  }
+  for (int i = 0; i < 4; ++i) {
+    const std::string s = P + "decoder.linear_blocks." + std::to_string(i);
+    NEED(sw, s + ".weight", 128, 256);
+    NEED(sb, s + ".bias", 128);
+    d.skip_t[i] = put(256 * 128);
+    transpose_into(&ar[d.skip_t[i]], sw->data.data(), 128, 256);
+    d.bskip[i] = put(128);
+    std::memcpy(&ar[d.bskip[i]], sb->data.data(), 128 * 4);
+  }
+  NEED(nw, P + "decoder.norm.weight", 128);
+  NEED(nb, P + "decoder.norm.bias", 128);
+  d.norm = put(256);
+  std::memcpy(&ar[d.norm], nw->data.data(), 128 * 4);
+  std::memcpy(&ar[d.norm + 128], nb->data.data(), 128 * 4);
+  NEED(fw, P + "final_layer.weight", kFeats, 128);
+  NEED(fb, P + "final_layer.bias", kFeats);
+  d.final_t = put(128 * 336);   // [128][336], columns 333..335 zero
+  for (int k = 0; k < 128; ++k)
+    for (int n = 0; n < kFeats; ++n) ar[d.final_t + static_cast<size_t>(k) * 336 + n] = fw->data[static_cast<size_t>(n) * 128 + k];
+  d.bfinal = put(336);
+  std::memcpy(&ar[d.bfinal], fb->data.data(), kFeats * 4);
+  NEED(pe, P + "query_pos_decoder.pe", 500, 1, 128);
+  d.pe = put(500 * 128);
+  std::memcpy(&ar[d.pe], pe->data.data(), 500 * 128 * 4);
+  CU(d.arena.ensure(ar.size()));
+  CU(cudaMemcpyAsync(d.arena.p, ar.data(), ar.size() * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  d.ready = true;
+  return AMUSE_OK;
+}
+
+bool any_with_prefix(amuse_ctx* ctx, const char* pre) {
+  const size_t n = std::strlen(pre);
+  for (auto& kv : ctx->raw)
+    if (kv.first.compare(0, n, pre) == 0) return true;
+  return false;
+}
+
+int choose_S(int B) {   // clips per 8-CTA cluster: fill ~16 clusters (128 SMs) first, then up to 4 clips each
+  int S = (B + 15) / 16;
+  if (S < 1) S = 1;
+  if (S > dn::kSMax) S = dn::kSMax;
+  return S;
+}
+
+int run_denoise(amuse_ctx* ctx, int B, Schedule& sc, int clip, const float* latents0, const float* z_con,
+                const float* z_emo, const float* z_sty, const float* step_noise, uint64_t seed,
+                uint64_t elem_base, float* latents_out, cudaStream_t st) {
+  DenW& d = ctx->den;
+  CU(ctx->cond.ensure(static_cast<size_t>(B) * 3 * 128));
+  CondArgs ca{};
+  int nc = 0;
+  const float* zs[3] = {z_con, z_emo, z_sty};
+  for (int i = 0; i < 3; ++i) {
+    if (!zs[i]) continue;
+    ca.z[nc] = zs[i];
+    ca.wt[nc] = d.misc.p + d.condw[i];
+    ca.bias[nc] = d.misc.p + d.condb[i];
+    ++nc;
+  }
+  ca.pe = d.misc.p + d.pe;
+  ca.out = ctx->cond.p;
+  CU(launch_cond_tokens(ca, B, nc, st));   // a4 (+a5): once per call, step-invariant
+  ctx->launches++;
+
+  dn::Params p{};
+  p.blob = d.blob.p;
+  p.temb = sc.d_temb;
+  p.cond = ctx->cond.p;
+  p.pe01 = d.misc.p + d.pe;
+  p.final_norm = d.misc.p + d.fnorm;
+  p.latents0 = latents0;
+  p.step_noise = step_noise;
+  p.coef = sc.d_coef;
+  p.latents_out = latents_out;
+  p.prof = (ctx->prof_step >= 0) ? ctx->d_prof : nullptr;
+  p.prof_step = ctx->prof_step;
+  p.B = B;
+  p.S = choose_S(B);
+  p.T = 2 + nc;
+  p.n_steps = sc.n_steps;
+  p.dir_uses_eps = sc.dir_uses_eps ? 1 : 0;
+  p.clip = clip;
+  p.seed = seed;
+  p.seed_elem_base = elem_base;
+  CU(dn::launch(p, st));
+  ctx->launches++;
+  ctx->prof_step = -1;
+  return AMUSE_OK;
+}
+
+int reserve_decode(amuse_ctx* ctx, int B) {
+  const size_t Mc = static_cast<size_t>(std::min(B, ctx->dec_chunk)) * kFrames;
+  CU(ctx->dXA.ensure(Mc * 128));
+  CU(ctx->dXB.ensure(Mc * 128));
+  CU(ctx->dXC.ensure(Mc * 128));
+  CU(ctx->dQKV.ensure(Mc * 384));
+  CU(ctx->dO.ensure(Mc * 128));
+  CU(ctx->dH.ensure(Mc * 512));
+  CU(ctx->dSkip.ensure(Mc * 128 * 4));
+  CU(ctx->dFeats.ensure(Mc * kFeats));
+  CU(ctx->dCvec.ensure(static_cast<size_t>(9) * B * 128));
+  if (!ctx->dZero.p) {
+    CU(ctx->dZero.ensure(128));
+    CU(cudaMemset(ctx->dZero.p, 0, 128 * sizeof(float)));
+  }
+  return AMUSE_OK;
+}
+
+// MotionPrior.decode (vae.py:216-278) + 6D -> axis-angle (infer_ldm.py:165-174).
+// Buffer plan per chunk of clips (no kernel ever reads and writes the same buffer):
+//   layer input  cur : XB (l = 0: broadcast PE) | SK[l-1] (l = 1..4) | XC (l >= 5, skip-linear output)
+//   after attention y: XA        layer output: SK[l] (l < 4, the skip stack) | XB (l >= 4)
+int run_decode(amuse_ctx* ctx, int B, const float* latents, float* feats6d, float* poses, float* trans,
+               cudaStream_t st) {
+  using namespace dec;
+  DecW& d = ctx->dec;
+  const float* W = d.arena.p;
+  if (int rc = reserve_decode(ctx, B)) return rc;
+  const int chunk = ctx->dec_chunk;
+  const size_t Mc = static_cast<size_t>(std::min(B, chunk)) * kFrames;
+  float* XA = ctx->dXA.p;
+  float* XB = ctx->dXB.p;
+  float* XC = ctx->dXC.p;
+  auto SK = [&](int i) { return ctx->dSkip.p + static_cast<size_t>(i) * Mc * 128; };
+
+  // collapsed 1-key cross attention of all 9 layers for the whole batch
+  CU(launch_cross_vectors(latents, W + d.wv_t, W + d.bv, W + d.wco_t, W + d.bco, ctx->dCvec.p, B, st));
+  ctx->launches++;
+
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nb = std::min(chunk, B - b0);
+    const int M = nb * kFrames;
+    CU(launch_broadcast_rows(W + d.pe, XB, nb, kFrames, st));   // queries = zeros + pe[:300] (vae.py:221,253)
+    ctx->launches++;
+    const float* cur = XB;
+    for (int l = 0; l < 9; ++l) {
+      const DecLayerW& L = d.L[l];
+      GemmArgs g{};
+      if (l >= 5) {   // x = Linear(cat(x, xs.pop()))  (cross_attention.py:115-117)
+        g.A = cur; g.lda = 128;
+        g.A2 = SK(8 - l); g.lda2 = 128;
+        g.Wt = W + d.skip_t[l - 5]; g.ldw = 128; g.bias = W + d.bskip[l - 5];
+        g.C = XC; g.ldc = 128; g.M = M; g.N = 128; g.K = 256;
+        CU(launch_gemm(EPI_BIAS, g, st));
+        ctx->launches++;
+        cur = XC;
+      }
+      // self attention: packed in_proj (q pre-scaled), per-head softmax(q k^T) v
+      g = GemmArgs{};
+      g.A = cur; g.lda = 128; g.Wt = W + L.wqkv_t; g.ldw = 384; g.bias = W + L.bqkv;
+      g.C = ctx->dQKV.p; g.ldc = 384; g.M = M; g.N = 384; g.K = 128;
+      CU(launch_gemm(EPI_QKV, g, st));
+      CU(launch_self_attention(ctx->dQKV.p, ctx->dO.p, nb, kFrames, st));
+      // y = norm2(norm1(x + out_proj(o)) + cross_vector)
+      g = GemmArgs{};
+      g.A = ctx->dO.p; g.lda = 128; g.Wt = W + L.wo_t; g.ldw = 128; g.bias = W + L.bo;
+      g.C = XA; g.ldc = 128; g.M = M; g.N = 128; g.K = 128;
+      g.R = cur; g.ldr = 128; g.ln_g = W + L.ln1; g.ln_b = W + L.ln1 + 128;
+      g.cvec = ctx->dCvec.p + (static_cast<size_t>(l) * B + b0) * 128;
+      g.ln2_g = W + L.ln2; g.ln2_b = W + L.ln2 + 128; g.rows_per_clip = kFrames;
+      CU(launch_gemm(EPI_RES_LN_CROSS_LN, g, st));
+      // h = gelu(linear1(y));  out = norm3(y + linear2(h))   [+ decoder.norm after the last block]
+      g = GemmArgs{};
+      g.A = XA; g.lda = 128; g.Wt = W + L.w1_t; g.ldw = 512; g.bias = W + L.b1;
+      g.C = ctx->dH.p; g.ldc = 512; g.M = M; g.N = 512; g.K = 128;
+      CU(launch_gemm(EPI_GELU, g, st));
+      float* out = (l < 4) ? SK(l) : XB;
+      g = GemmArgs{};
+      g.A = ctx->dH.p; g.lda = 512; g.Wt = W + L.w2_t; g.ldw = 128; g.bias = W + L.b2;
+      g.C = out; g.ldc = 128; g.M = M; g.N = 128; g.K = 512;
+      g.R = XA; g.ldr = 128; g.ln_g = W + L.ln3; g.ln_b = W + L.ln3 + 128;
+      if (l == 8) {   // SkipTransformerDecoder.norm (cross_attention.py:122-123) folded in: LN(LN3(..) + 0)
+        g.cvec = ctx->dZero.p; g.rows_per_clip = 1 << 30;
+        g.ln2_g = W + d.norm; g.ln2_b = W + d.norm + 128;
+        CU(launch_gemm(EPI_RES_LN_CROSS_LN, g, st));
+      } else {
+        CU(launch_gemm(EPI_RES_LN, g, st));
+      }
+      ctx->launches += 5;
+      cur = out;
+    }
+    // final_layer 128 -> 333 (vae.py:272), then 6D -> axis-angle + trans
+    float* feats = feats6d ? feats6d + static_cast<size_t>(b0) * kFrames * kFeats : ctx->dFeats.p;
+    GemmArgs g{};
+    g.A = cur; g.lda = 128; g.Wt = W + d.final_t; g.ldw = 336; g.bias = W + d.bfinal;
+    g.C = feats; g.ldc = kFeats; g.M = M; g.N = kFeats; g.K = 128;
+    CU(launch_gemm(EPI_BIAS, g, st));
+    ctx->launches++;
+    if (poses) {
+      CU(launch_rot6d(feats, kFeats, static_cast<long long>(M), poses + static_cast<size_t>(b0) * kFrames * 165,
+                      trans ? trans + static_cast<size_t>(b0) * kFrames * 3 : nullptr, st));
+      ctx->launches++;
+    }
+  }
+  return AMUSE_OK;
+}
+
+int check_ready(amuse_ctx* ctx, bool den, bool dec) {
+  if (!ctx) return AMUSE_E_INVALID;
+  if (den && !ctx->den.ready) return fail(ctx, AMUSE_E_STATE, "denoiser weights not finalized");
+  if (dec && !ctx->dec.ready) return fail(ctx, AMUSE_E_STATE, "vae decoder weights not finalized");
+  return AMUSE_OK;
+}
+
+}  // namespace
+
+// =========================================================================== extern "C"
+extern "C" {
+
+const char* amuse_version(void) { return "amuse_b200 0.1 (sm_100a)"; }
+
+int amuse_create(amuse_ctx** out, int device_ordinal) {
+  if (!out) return AMUSE_E_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device_ordinal < 0 || device_ordinal >= n) return AMUSE_E_CUDA;
+  if (cudaSetDevice(device_ordinal) != cudaSuccess) return AMUSE_E_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess) return AMUSE_E_CUDA;
+  if (prop.major != 10) return AMUSE_E_UNSUPPORTED;   // sm_100a code only
+  amuse_ctx* c = new amuse_ctx();
+  c->device = device_ordinal;
+  default_alphas(c->alphas_cumprod);
+  if (cudaMalloc(&c->d_prof, 128 * sizeof(long long)) != cudaSuccess) {
+    delete c;
+    return AMUSE_E_CUDA;
+  }
+  cudaMemset(c->d_prof, 0, 128 * sizeof(long long));
+  *out = c;
+  return AMUSE_OK;
+}
+
+void amuse_destroy(amuse_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  drop_schedules(ctx);
+  DevBuf* bufs[] = {&ctx->den.blob, &ctx->den.misc, &ctx->dec.arena, &ctx->cond, &ctx->lat_tmp, &ctx->lat_out,
+                    &ctx->one_coef, &ctx->dXA, &ctx->dXB, &ctx->dXC, &ctx->dQKV, &ctx->dO, &ctx->dH, &ctx->dSkip,
+                    &ctx->dFeats, &ctx->dCvec, &ctx->dZero, &ctx->h2d};
+  for (DevBuf* b : bufs) b->release();
+  ast::release(ctx->astw);
+  if (ctx->d_prof) cudaFree(ctx->d_prof);
+  delete ctx;
+}
+
+const char* amuse_last_error(amuse_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int amuse_load_weights(amuse_ctx* ctx, const char* name, const void* data, const int64_t* shape, int ndim,
+                       int dtype) {
+  if (!ctx || !name || !data || !shape || ndim < 0 || ndim > 8) return fail(ctx, AMUSE_E_INVALID, "bad argument");
+  if (dtype != AMUSE_DTYPE_F32) return fail(ctx, AMUSE_E_UNSUPPORTED, "only fp32 weights are supported");
+  cudaSetDevice(ctx->device);
+  std::string key(name);
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= shape[i];
+  if (key.compare(0, 4, "ast.") == 0) {   // 1 GB of encoder weights stays on the device
+    int rc = ast::stage(ctx->astw, key.substr(4), data, shape, ndim);
+    if (rc) return fail(ctx, rc, "ast weight '%s' rejected", name);
+    return AMUSE_OK;
+  }
+  if (key == "scheduler.alphas_cumprod") {
+    ctx->alphas_cumprod.resize(static_cast<size_t>(n));
+    CU(cudaMemcpy(ctx->alphas_cumprod.data(), data, static_cast<size_t>(n) * 4, cudaMemcpyDefault));
+    drop_schedules(ctx);
+    return AMUSE_OK;
+  }
+  if (key.compare(0, 9, "denoiser.") != 0 && key.compare(0, 4, "vae.") != 0)
+    return fail(ctx, AMUSE_E_INVALID, "unknown weight namespace in '%s'", name);
+  if (key.compare(0, 12, "vae.encoder.") == 0 || key == "vae.global_motion_token" ||
+      key.compare(0, 19, "vae.skel_embedding.") == 0 || key == "vae.query_pos_encoder.pe" ||
+      key == "denoiser.mem_pos.pe")
+    return AMUSE_OK;   // not on the sampling path
+  HostTensor t;
+  t.shape.assign(shape, shape + ndim);
+  t.data.resize(static_cast<size_t>(n));
+  CU(cudaMemcpy(t.data.data(), data, static_cast<size_t>(n) * 4, cudaMemcpyDefault));
+  ctx->raw[key] = std::move(t);
+  return AMUSE_OK;
+}
+
+int amuse_finalize_weights(amuse_ctx* ctx, void* stream) {
+  if (!ctx) return AMUSE_E_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  bool any = false;
+  if (any_with_prefix(ctx, "denoiser.")) {
+    if (int rc = pack_denoiser(ctx, st)) return rc;
+    any = true;
+  }
+  if (any_with_prefix(ctx, "vae.")) {
+    if (int rc = pack_decoder(ctx, st)) return rc;
+    any = true;
+  }
+  if (ast::staged(ctx->astw)) {
+    int rc = ast::finalize(ctx->astw, st);
+    if (rc) return fail(ctx, rc, "ast finalize: %s", ast::last_error(ctx->astw));
+    any = true;
+  }
+  if (!any) return fail(ctx, AMUSE_E_MISSING, "no weights loaded");
+  return AMUSE_OK;
+}
+
+int amuse_reserve(amuse_ctx* ctx, int max_clips, int max_steps) {
+  if (!ctx || max_clips < 1) return fail(ctx, AMUSE_E_INVALID, "bad argument");
+  (void)max_steps;
+  cudaSetDevice(ctx->device);
+  CU(ctx->cond.ensure(static_cast<size_t>(max_clips) * 3 * 128));
+  CU(ctx->lat_out.ensure(static_cast<size_t>(max_clips) * 128));
+  if (ctx->dec.ready)
+    if (int rc = reserve_decode(ctx, max_clips)) return rc;
+  return AMUSE_OK;
+}
+
+int amuse_schedule(amuse_ctx* ctx, int n_steps, int sampler, float eta, int32_t* timesteps, float* coef) {
+  if (!ctx) return AMUSE_E_INVALID;
+  Schedule sc;
+  if (int rc = build_schedule(ctx, n_steps, sampler, eta, sc)) return rc;
+  if (timesteps) std::memcpy(timesteps, sc.timesteps.data(), sizeof(int32_t) * n_steps);
+  if (coef) std::memcpy(coef, sc.coef.data(), sizeof(float) * 5 * n_steps);
+  return AMUSE_OK;
+}
+
+int amuse_denoise(amuse_ctx* ctx, int B, int n_steps, int sampler, float eta, int clip_sample, const float* latents0,
+                  const float* z_con, const float* z_emo, const float* z_sty, const float* step_noise,
+                  uint64_t seed, float* latents_out, void* stream) {
+  if (int rc = check_ready(ctx, true, false)) return rc;
+  if (B < 1 || !latents0 || !z_con || !latents_out) return fail(ctx, AMUSE_E_INVALID, "bad argument");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Schedule* sc = nullptr;
+  if (int rc = get_schedule(ctx, n_steps, sampler, eta, st, &sc)) return rc;
+  const int clip = (clip_sample < 0) ? (sampler == AMUSE_SAMPLER_DDIM ? 1 : 0) : (clip_sample != 0);
+  return run_denoise(ctx, B, *sc, clip, latents0, z_con, z_emo, z_sty, step_noise, seed, 0, latents_out, st);
+}
+
+int amuse_denoiser_eps(amuse_ctx* ctx, int B, int timestep, const float* sample, const float* z_con,
+                       const float* z_emo, const float* z_sty, float* eps_out, void* stream) {
+  if (int rc = check_ready(ctx, true, false)) return rc;
+  if (B < 1 || !sample || !z_con || !eps_out) return fail(ctx, AMUSE_E_INVALID, "bad argument");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // a one-step "schedule" whose update returns eps itself: x0 = x, x' = 0*x0 + 1*eps
+  Schedule sc;
+  sc.n_steps = 1;
+  sc.timesteps = {timestep};
+  sc.coef = {1.f, 0.f, 0.f, 1.f, 0.f};
+  sc.dir_uses_eps = true;
+  CU(cudaMalloc(&sc.d_timesteps, sizeof(int)));
+  CU(cudaMalloc(&sc.d_coef, 5 * sizeof(float)));
+  CU(cudaMalloc(&sc.d_temb, 128 * sizeof(float)));
+  CU(cudaMemcpyAsync(sc.d_timesteps, sc.timesteps.data(), sizeof(int), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(sc.d_coef, sc.coef.data(), 5 * sizeof(float), cudaMemcpyHostToDevice, st));
+  const float* m = ctx->den.misc.p;
+  CU(launch_time_table(sc.d_timesteps, 1, m + ctx->den.freqs, m + ctx->den.w1t, m + ctx->den.b1, m + ctx->den.w2t,
+                       m + ctx->den.b2, sc.d_temb, st));
+  ctx->launches++;
+  int rc = run_denoise(ctx, B, sc, 0, sample, z_con, z_emo, z_sty, nullptr, 0, 0, eps_out, st);
+  cudaStreamSynchronize(st);
+  cudaFree(sc.d_timesteps);
+  cudaFree(sc.d_coef);
+  cudaFree(sc.d_temb);
+  return rc;
+}
+
+int amuse_decode(amuse_ctx* ctx, int B, const float* latents, float* feats6d, float* poses, float* trans,
+                 void* stream) {
+  if (int rc = check_ready(ctx, false, true)) return rc;
+  if (B < 1 || !latents || (!feats6d && !poses)) return fail(ctx, AMUSE_E_INVALID, "bad argument");
+  cudaSetDevice(ctx->device);
+  return run_decode(ctx, B, latents, feats6d, poses, trans, static_cast<cudaStream_t>(stream));
+}
+
+int amuse_rot6d_to_axis_angle(amuse_ctx* ctx, int64_t n, const float* d6, float* axis_angle, void* stream) {
+  if (!ctx || n < 0 || !d6 || !axis_angle) return fail(ctx, AMUSE_E_INVALID, "bad argument");
+  if (n == 0) return AMUSE_OK;
+  cudaSetDevice(ctx->device);
+  CU(launch_rot6d_flat(d6, n, axis_angle, static_cast<cudaStream_t>(stream)));
+  ctx->launches++;
+  return AMUSE_OK;
+}
+
+int amuse_diffusion_backward(amuse_ctx* ctx, int B, int n_steps, int sampler, float eta, int clip_sample,
+                             const float* latents0, const float* z_con, const float* z_emo, const float* z_sty,
+                             const float* step_noise, uint64_t seed, float* latents_out, float* feats6d,
+                             float* poses, float* trans, void* stream) {
+  if (int rc = check_ready(ctx, true, true)) return rc;
+  if (!poses) return fail(ctx, AMUSE_E_INVALID, "poses must not be NULL");
+  cudaSetDevice(ctx->device);
+  float* z = latents_out;
+  if (!z) {
+    CU(ctx->lat_out.ensure(static_cast<size_t>(B) * 128));
+    z = ctx->lat_out.p;
+  }
+  if (int rc = amuse_denoise(ctx, B, n_steps, sampler, eta, clip_sample, latents0, z_con, z_emo, z_sty, step_noise,
+                             seed, z, stream))
+    return rc;
+  return run_decode(ctx, B, z, feats6d, poses, trans, static_cast<cudaStream_t>(stream));
+}
+
+int amuse_diffusion_backward_host(amuse_ctx* ctx, int B, int n_steps, int sampler, float eta, int clip_sample,
+                                  const float* latents0, const float* z_con, const float* z_emo,
+                                  const float* z_sty, const float* step_noise, uint64_t seed, float* poses,
+                                  float* trans, void* stream) {
+  if (int rc = check_ready(ctx, true, true)) return rc;
+  if (B < 1 || !latents0 || !z_con || !poses) return fail(ctx, AMUSE_E_INVALID, "bad argument");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t nl = static_cast<size_t>(B) * 128, nz = static_cast<size_t>(B) * 256;
+  const size_t nn = step_noise ? static_cast<size_t>(n_steps) * B * 128 : 0;
+  const size_t np = static_cast<size_t>(B) * kFrames * 165, nt = static_cast<size_t>(B) * kFrames * 3;
+  CU(ctx->h2d.ensure(nl + 3 * nz + nn + np + nt));
+  float* d_l0 = ctx->h2d.p;
+  float* d_con = d_l0 + nl;
+  float* d_emo = d_con + nz;
+  float* d_sty = d_emo + nz;
+  float* d_noise = d_sty + nz;
+  float* d_poses = d_noise + nn;
+  float* d_trans = d_poses + np;
+  CU(cudaMemcpyAsync(d_l0, latents0, nl * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_con, z_con, nz * 4, cudaMemcpyHostToDevice, st));
+  if (z_emo) CU(cudaMemcpyAsync(d_emo, z_emo, nz * 4, cudaMemcpyHostToDevice, st));
+  if (z_sty) CU(cudaMemcpyAsync(d_sty, z_sty, nz * 4, cudaMemcpyHostToDevice, st));
+  if (step_noise) CU(cudaMemcpyAsync(d_noise, step_noise, nn * 4, cudaMemcpyHostToDevice, st));
+  if (int rc = amuse_diffusion_backward(ctx, B, n_steps, sampler, eta, clip_sample, d_l0, d_con,
+                                        z_emo ? d_emo : nullptr, z_sty ? d_sty : nullptr,
+                                        step_noise ? d_noise : nullptr, seed, nullptr, nullptr, d_poses, d_trans,
+                                        stream))
+    return rc;
+  CU(cudaMemcpyAsync(poses, d_poses, np * 4, cudaMemcpyDeviceToHost, st));
+  if (trans) CU(cudaMemcpyAsync(trans, d_trans, nt * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return AMUSE_OK;
+}
+
+int amuse_ast_features(amuse_ctx* ctx, int B, const float* fbank, float* con, float* emo, float* sty, void* stream) {
+  if (!ctx || B < 1 || !fbank || !con || !emo || !sty) return fail(ctx, AMUSE_E_INVALID, "bad argument");
+  if (!ast::ready(ctx->astw)) return fail(ctx, AMUSE_E_STATE, "ast weights not finalized");
+  cudaSetDevice(ctx->device);
+  int64_t launches = 0;
+  int rc = ast::forward(ctx->astw, B, fbank, con, emo, sty, static_cast<cudaStream_t>(stream), &launches);
+  ctx->launches += launches;
+  if (rc) return fail(ctx, rc, "ast forward: %s", ast::last_error(ctx->astw));
+  return AMUSE_OK;
+}
+
+int64_t amuse_launch_count(amuse_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int amuse_profile_arm(amuse_ctx* ctx, int step) {
+  if (!ctx) return AMUSE_E_INVALID;
+  ctx->prof_step = step;
+  return AMUSE_OK;
+}
+int amuse_profile_read(amuse_ctx* ctx, int64_t* stamps, int n) {
+  if (!ctx || !stamps || n < 1 || n > 128) return fail(ctx, AMUSE_E_INVALID, "bad argument");
+  cudaSetDevice(ctx->device);
+  CU(cudaMemcpy(stamps, ctx->d_prof, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+  return AMUSE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+// Interface of the persistent denoise-loop kernel (K1 + K2 of SURVEY.md section 2.2).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace amuse {
+namespace dn {
+
+constexpr int kCluster = 8;            // CTAs per thread-block cluster (one cluster = up to kSMax clips)
+constexpr int kThreads = 256;
+constexpr int kSMax = 4;               // clips per cluster
+constexpr int kTMax = 5;               // tokens per clip: z, t, con, emo, sty (denoiser.py:174,180)
+constexpr int kRMax = kSMax * kTMax;   // activation rows per cluster
+constexpr int kTilesPerStep = 40;      // 9 layers x 4 weight tiles + 4 skip-linear tiles
+
+// Per-CTA-rank weight stream ("blob"): the tiles one CTA consumes during one denoiser
+// evaluation, in consumption order, each tile K-major ([k][n_local]) followed by the
+// bias / LayerNorm vectors its epilogue needs.  Sizes in floats.
+constexpr int kTileQKV = 128 * 96 + 96;          // in_proj rows of one head: q|k|v 32 each  + bias
+constexpr int kTileWO = 32 * 128 + 128 + 256;    // out_proj columns of one head (K-split)   + bias + norm1
+constexpr int kTileW1 = 128 * 64 + 64;           // linear1 rows [64*rank, +64)              + bias
+constexpr int kTileW2 = 64 * 128 + 128 + 256;    // linear2 columns [64*rank, +64) (K-split) + bias + norm2
+constexpr int kTileSK = 256 * 16 + 16;           // linear_blocks rows [16*rank, +16)        + bias
+constexpr int kLayerFloats = kTileQKV + kTileWO + kTileW1 + kTileW2;
+constexpr int kBlobRankFloats = 9 * kLayerFloats + 4 * kTileSK;
+
+__host__ __device__ inline void tile_info(int i, int& off, int& n) {
+  // i in [0, 40): layers 0..4 have 4 tiles, layers 5..8 have 5 (skip-linear first)
+  int l, j;
+  if (i < 20) {
+    l = i >> 2;
+    j = i & 3;
+    off = l * kLayerFloats;
+  } else {
+    l = 5 + (i - 20) / 5;
+    j = (i - 20) % 5 - 1;   // -1 = skip tile
+    off = 5 * kLayerFloats + (l - 5) * (kLayerFloats + kTileSK);
+    if (j < 0) {
+      n = kTileSK;
+      return;
+    }
+    off += kTileSK;
+  }
+  const int sz[4] = {kTileQKV, kTileWO, kTileW1, kTileW2};
+  for (int q = 0; q < j; ++q) off += sz[q];
+  n = sz[j];
+}
+
+struct Params {
+  const float* blob;         // [kCluster][kBlobRankFloats]
+  const float* temb;         // [n_steps][128]   time tokens (a3), batch-invariant
+  const float* cond;         // [B][3][128]      condition tokens + their PE rows (a4+a5); first T-2 valid
+  const float* pe01;         // [2][128]         query_pos.pe rows 0 and 1
+  const float* final_norm;   // [256]            encoder.norm weight | bias
+  const float* latents0;     // [B][128]
+  const float* step_noise;   // nullable [n_steps][B][128]
+  const float* coef;         // [n_steps][5]     sqrt(a), sqrt(1-a), c_x0, c_dir, sigma
+  float* latents_out;        // [B][128]
+  long long* prof;           // nullable: clock64 stamps of cluster 0 / rank 0 (debug)
+  int B, S, T, n_steps;
+  int dir_uses_eps;          // 1: x' = c2 x0 + c3 eps (DDIM);  0: x' = c2 x0 + c3 x (DDPM posterior mean)
+  int clip;                  // clamp x0 to [-1, 1]
+  unsigned long long seed;   // Philox seed when step_noise == nullptr and sigma > 0
+  unsigned long long seed_elem_base;   // global index of this launch's first latent element (multi-GPU shards)
+  int prof_step;
+};
+
+size_t smem_bytes();
+cudaError_t launch(const Params& p, cudaStream_t stream);
+
+}  // namespace dn
+}  // namespace amuse

@@ -1,0 +1,197 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against
+  (1) the committed golden vectors produced by the REFERENCE'S OWN modules (oracle/make_golden.py),
+  (2) the CPU oracle (oracle/lpdm_ref.py) run live on odd batch sizes / ablations.
+
+Tolerances.  All arithmetic is fp32.  The yardstick is the fp64 run of the same reference
+modules: the reference's own fp32 path is `ref_err` away from it, and the CUDA path must be within
+max(ABS_FLOOR, K * ref_err) of the fp64 result and within TOL32 of the reference fp32 result.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lpdm_ref as R
+from oracle import weights as W
+
+pytestmark = pytest.mark.gpu
+
+TOL_EPS = 2e-5          # one Denoiser.forward, |eps| ~ 3
+TOL_LAT_DDIM = 2e-4     # 50 recurrent steps with clamp; reference fp32-vs-fp64 itself is ~3e-5
+TOL_FEATS = 2e-4        # 6D features, |feats| ~ 3
+TOL_GEO_DEG = 0.05      # rotation geodesic, degrees
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def _report(name, got, ref32, ref64):
+    got = got.double().cpu()
+    e64 = (got - _t(ref64).double()).abs().max().item()
+    e32 = (got - _t(ref32).double()).abs().max().item()
+    r = (_t(ref32).double() - _t(ref64).double()).abs().max().item()
+    print(f"[parity] {name}: |cuda-f64|={e64:.3e} |cuda-f32ref|={e32:.3e} |f32ref-f64|={r:.3e}")
+    return e64, e32, r
+
+
+def test_weights_regenerate(golden_dir, synthetic_weights):
+    g = np.load(golden_dir / "denoiser_step.npz")
+    assert W.checksum(synthetic_weights["denoiser"]) == str(g["denoiser_sha1"])
+    assert W.checksum(synthetic_weights["vae"]) == str(g["motionprior_sha1"])
+
+
+def test_denoiser_eps_golden(engine, golden_dir):
+    g = np.load(golden_dir / "denoiser_step.npz")
+    x, con, emo, sty = (_t(g[k]) for k in ("x", "con", "emo", "sty"))
+    for t in (981, 500, 1):
+        got = engine.denoiser_eps(x, t, con, emo, sty)
+        e64, e32, r = _report(f"eps t={t}", got, g[f"eps_t{t}_f32"], g[f"eps_t{t}_f64"])
+        assert e64 < max(TOL_EPS, 4 * r) and e32 < TOL_EPS
+    got = engine.denoiser_eps(x, 981, con, None, None)
+    e64, e32, r = _report("eps no emo/sty", got, g["eps_t981_noemo_nosty_f32"], g["eps_t981_noemo_nosty_f64"])
+    assert e64 < max(TOL_EPS, 4 * r) and e32 < TOL_EPS
+    got = engine.denoiser_eps(x, 981, con, emo, None)
+    e64, e32, r = _report("eps no sty", got, g["eps_t981_nosty_f32"], g["eps_t981_nosty_f64"])
+    assert e64 < max(TOL_EPS, 4 * r) and e32 < TOL_EPS
+
+
+@pytest.mark.parametrize("name", ["ddim50_b4", "ddim1_b1", "ddim50_b1"])
+def test_ddim_golden(engine, golden_dir, name):
+    g = np.load(golden_dir / f"{name}.npz")
+    got = engine.denoise(_t(g["latents0"]), _t(g["con"]), _t(g["emo"]), _t(g["sty"]), n_steps=int(g["n_steps"]),
+                         sampler="ddim")
+    e64, e32, r = _report(name, got, g["z_f32"], g["z_f64"])
+    assert e64 < max(TOL_LAT_DDIM, 4 * r) and e32 < TOL_LAT_DDIM
+
+
+@pytest.mark.parametrize("name", ["ddpm100_b2", "ddpm1000_b2"])
+def test_ddpm_golden(engine, golden_dir, name):
+    g = np.load(golden_dir / f"{name}.npz")
+    n, B = int(g["n_steps"]), g["latents0"].shape[0]
+    noise = torch.randn(n, B, 128, generator=torch.Generator().manual_seed(int(g["noise_seed"])))
+    if "noise_probe" in g:
+        assert torch.equal(noise[[0, 499, 999]], _t(g["noise_probe"])), "torch CPU RNG stream differs from the fixture's"
+    got = engine.denoise(_t(g["latents0"]), _t(g["con"]), _t(g["emo"]), _t(g["sty"]), n_steps=n, sampler="ddpm",
+                         step_noise=noise)
+    e64, e32, r = _report(name, got, g["z_f32"], g["z_f64"])
+    scale = float(np.abs(g["z_f64"]).max())          # unclipped ancestral chains of a random net grow large
+    assert e64 < max(2e-5 * scale, 4 * r) and e32 < max(2e-5 * scale, 4 * r)
+
+
+def test_decode_golden(engine, golden_dir):
+    g = np.load(golden_dir / "decode_b2.npz")
+    idx = g["frame_idx"]
+    poses, trans, feats = engine.decode(_t(g["z"]), want_feats=True)
+    e64, e32, r = _report("decode feats", feats[:, idx], g["feats_f32"], g["feats_f64"])
+    assert e64 < max(TOL_FEATS, 4 * r) and e32 < TOL_FEATS
+    geo = R.geodesic_deg(poses[:, idx].cpu(), _t(g["poses_f64"]))
+    print(f"[parity] decode poses geodesic max {geo.max().item():.4f} deg")
+    assert geo.max().item() < TOL_GEO_DEG
+    assert torch.equal(trans.cpu(), feats[:, :, -3:].cpu())
+
+
+def test_backward_golden(engine, golden_dir):
+    g = np.load(golden_dir / "backward_ddim50_b2.npz")
+    idx = g["frame_idx"]
+    out = engine.diffusion_backward(_t(g["latents0"]), _t(g["con"]), _t(g["emo"]), _t(g["sty"]), n_steps=50,
+                                    sampler="ddim", want_latents=True, want_feats=True)
+    e64, e32, r = _report("backward latents", out["latents"], g["z_f32"], g["z_f64"])
+    assert e64 < max(TOL_LAT_DDIM, 4 * r)
+    e64, e32, r = _report("backward feats", out["feats"][:, idx], g["feats_f32"], g["feats_f64"])
+    assert e64 < max(TOL_FEATS, 4 * r)
+    geo = R.geodesic_deg(out["poses"][:, idx].cpu(), _t(g["poses_f64"]))
+    print(f"[parity] backward poses geodesic max {geo.max().item():.4f} deg")
+    assert geo.max().item() < TOL_GEO_DEG
+    # SMPL-X pose L2 (north_star): on the 6D rotation features, per value RMS
+    l2 = (out["feats"][:, idx].double().cpu() - _t(g["feats_f64"])).pow(2).mean().sqrt().item()
+    print(f"[parity] backward 6D feats RMS error {l2:.3e}")
+    assert l2 < 1e-4
+
+
+def test_rot6d_cases(engine, golden_dir):
+    g = np.load(golden_dir / "rot6d_cases.npz")
+    aa = engine.rot6d_to_axis_angle(_t(g["d6"])).cpu()
+    geo = R.geodesic_deg(aa, _t(g["aa_f64"]))
+    print(f"[parity] rot6d geodesic max {geo.max().item():.5f} deg")
+    assert geo.max().item() < 0.02
+    d = (aa - _t(g["aa_f32"])).abs()
+    ok = d.max(dim=-1).values < 1e-4          # identical up to 2*pi-wrap sign flips near pi
+    assert ok.float().mean().item() > 0.9
+
+
+@pytest.mark.parametrize("B,emo,sty", [(1, True, True), (3, True, True), (5, True, False), (7, False, False),
+                                        (13, True, True), (16, True, True), (17, True, True), (64, True, True)])
+def test_ddim_vs_oracle_live(engine, synthetic_weights, B, emo, sty):
+    """Odd batch sizes exercise every clips-per-cluster split (1..4 clips, uneven halves, partial
+    last cluster); None conditions exercise 3- and 4-token sequences."""
+    g = torch.Generator().manual_seed(1000 + B)
+    l0, con = torch.randn(B, 128, generator=g), torch.randn(B, 256, generator=g)
+    ze = torch.randn(B, 256, generator=g) if emo else None
+    zs = torch.randn(B, 256, generator=g) if sty else None
+    n = 10
+    ref = R.sample_latents(synthetic_weights["denoiser"], l0, con, ze, zs, n, "ddim")
+    got = engine.denoise(l0, con, ze, zs, n_steps=n, sampler="ddim").cpu()
+    err = (got - ref).abs().max().item()
+    print(f"[parity] live ddim10 B={B} emo={emo} sty={sty}: max|d|={err:.3e}")
+    assert err < 1e-4
+
+
+def test_eta_and_philox(engine, synthetic_weights):
+    """DDIM with eta > 0 against the oracle with injected noise; Philox path: reproducible,
+    seed-dependent, and independent of how clips are packed into clusters."""
+    B, n, eta = 6, 8, 0.5
+    g = torch.Generator().manual_seed(77)
+    l0, con = torch.randn(B, 128, generator=g), torch.randn(B, 256, generator=g)
+    ze, zs = torch.randn(B, 256, generator=g), torch.randn(B, 256, generator=g)
+    noise = torch.randn(n, B, 128, generator=g)
+    ts, coef = engine.schedule(n, "ddim", eta)
+    plan = {"timesteps": ts, "coef": coef, "clip": True, "sampler": "ddim"}
+    x = l0
+    for i, t in enumerate(ts):
+        e = R.denoiser_forward(synthetic_weights["denoiser"], x, t, con, ze, zs)
+        x = R.scheduler_step(plan, i, x, e, None) + coef[i, 4] * noise[i]
+    got = engine.denoise(l0, con, ze, zs, n_steps=n, sampler="ddim", eta=eta, step_noise=noise).cpu()
+    assert (got - x).abs().max().item() < 1e-4
+    a = engine.denoise(l0, con, ze, zs, n_steps=n, sampler="ddpm", seed=5).cpu()
+    b = engine.denoise(l0, con, ze, zs, n_steps=n, sampler="ddpm", seed=5).cpu()
+    c = engine.denoise(l0, con, ze, zs, n_steps=n, sampler="ddpm", seed=6).cpu()
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    a2 = engine.denoise(l0[:2], con[:2], ze[:2], zs[:2], n_steps=n, sampler="ddpm", seed=5).cpu()
+    assert torch.allclose(a[:2], a2, atol=1e-5)
+
+
+def test_schedule_matches_oracle(engine):
+    for n in (1, 50):
+        ts, coef = engine.schedule(n, "ddim")
+        plan = R.ddim_coeffs(n)
+        assert ts == plan["timesteps"]
+        assert torch.equal(coef, plan["coef"])
+    for n in (100, 1000):
+        ts, coef = engine.schedule(n, "ddpm")
+        plan = R.ddpm_coeffs(n)
+        assert ts == plan["timesteps"]
+        assert torch.equal(coef, plan["coef"])
+    with pytest.raises(Exception):
+        engine.schedule(1000, "ddim")          # alphas_cumprod[1000]: IndexError in the reference too
+
+
+def test_host_entry_point(engine, golden_dir):
+    g = np.load(golden_dir / "backward_ddim50_b2.npz")
+    idx = g["frame_idx"]
+    out = engine.diffusion_backward_host(_t(g["latents0"]).pin_memory(), _t(g["con"]).pin_memory(),
+                                         _t(g["emo"]).pin_memory(), _t(g["sty"]).pin_memory(), n_steps=50)
+    geo = R.geodesic_deg(out["poses"][:, idx], _t(g["poses_f64"]))
+    assert geo.max().item() < TOL_GEO_DEG
+
+
+def test_decode_chunking_and_full_size(engine, synthetic_weights):
+    """B larger than the decoder's chunk (32 clips) and not a multiple of it; compared clip-wise
+    with a B=1 run (batch invariance: every clip is independent)."""
+    B = 70
+    z = torch.randn(B, 128, generator=torch.Generator().manual_seed(5))
+    poses, trans, feats = engine.decode(z, want_feats=True)
+    for b in (0, 31, 32, 69):
+        p1, t1, f1 = engine.decode(z[b:b + 1], want_feats=True)
+        assert torch.equal(f1[0], feats[b])
+    ref = R.vae_decode(synthetic_weights["vae"], z[69:70])
+    assert (feats[69].cpu() - ref[0]).abs().max().item() < TOL_FEATS
