@@ -1,0 +1,66 @@
+"""Developer timing probe (not the bench contract): device-time of the sampler pieces + the
+in-kernel cycle profile of one denoiser step.  Usage: python scripts/quick_bench.py [B]"""
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from amuse_b200.engine import Engine          # noqa: E402
+from oracle import weights as W              # noqa: E402
+
+
+def timeit(fn, n=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return sorted(ts)[len(ts) // 2]
+
+
+def main():
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+    eng = Engine("cuda:0")
+    eng.load_state_dict("denoiser", W.denoiser_state_dict())
+    eng.load_state_dict("vae", W.motionprior_state_dict())
+    eng.finalize()
+    g = torch.Generator().manual_seed(0)
+    l0, con, emo, sty = (torch.randn(B, d, generator=g).cuda() for d in (128, 256, 256, 256))
+    noise = torch.randn(1000, B, 128, generator=g).cuda()
+    for n, samp in ((50, "ddim"), (1000, "ddpm")):
+        ms = timeit(lambda: eng.denoise(l0, con, emo, sty, n_steps=n, sampler=samp,
+                                        step_noise=noise if samp == "ddpm" else None), n=3, warm=1)
+        print(f"denoise B={B} {samp}{n}: {ms:.3f} ms  ({ms / n * 1000:.2f} us/step)")
+    z = eng.denoise(l0, con, emo, sty, n_steps=50)
+    ms = timeit(lambda: eng.decode(z))
+    print(f"decode B={B}: {ms:.3f} ms   ({B * 1.7595 / ms:.2f} TFLOP/s algorithmic)")
+    ms = timeit(lambda: eng.diffusion_backward(l0, con, emo, sty, n_steps=1000, sampler="ddpm", step_noise=noise), n=3, warm=1)
+    print(f"diffusion_backward B={B} ddpm1000: {ms:.3f} ms  -> {B * 300 / ms * 1000:.0f} frames/s")
+    ms = timeit(lambda: eng.diffusion_backward(l0, con, emo, sty, n_steps=50, sampler="ddim"), n=3, warm=1)
+    print(f"diffusion_backward B={B} ddim50:   {ms:.3f} ms  -> {B * 300 / ms * 1000:.0f} frames/s")
+    # in-kernel cycle stamps of step 3
+    eng.profile_arm(3)
+    eng.denoise(l0, con, emo, sty, n_steps=8)
+    st = eng.profile_read(96)
+    names = ["skip", "qkv", "attn", "oproj+sync1", "red+sync2", "ln1", "ffn1", "ffn2+sync3", "red+sync4", "ln2"]
+    print("step cycles total:", st[92] - st[0], " build-x:", st[1] - st[0])
+    for l in range(9):
+        base = 2 + l * 10
+        prev = st[1] if l == 0 else st[2 + (l - 1) * 10 + 9]
+        row = []
+        for j in range(10):
+            row.append(st[base + j] - (prev if j == 0 else st[base + j - 1]))
+        print(f"layer {l}: " + " ".join(f"{n}={c}" for n, c in zip(names, row)))
+    print("final+update:", st[92] - st[2 + 8 * 10 + 9])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,113 @@
+"""CPU tests of the oracle itself: (1) the restatement against the committed golden vectors
+(produced by the reference's own modules), everywhere; (2) against the reference modules imported
+live, in the build container only (/root/reference does not exist on the GPU box)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lpdm_ref as R
+from oracle import reference_loader as L
+from oracle import weights as W
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.fixture(scope="module")
+def sds(synthetic_weights):
+    d, v = synthetic_weights["denoiser"], synthetic_weights["vae"]
+    return d, v, R.cast_sd(d, torch.float64), R.cast_sd(v, torch.float64)
+
+
+def test_golden_checksums(golden_dir, synthetic_weights):
+    g = np.load(golden_dir / "denoiser_step.npz")
+    assert W.checksum(synthetic_weights["denoiser"]) == str(g["denoiser_sha1"])
+    assert W.checksum(synthetic_weights["vae"]) == str(g["motionprior_sha1"])
+
+
+def test_denoiser_step_golden(golden_dir, sds):
+    d32, _, d64, _ = sds
+    g = np.load(golden_dir / "denoiser_step.npz")
+    x, con, emo, sty = (_t(g[k]) for k in ("x", "con", "emo", "sty"))
+    for t in (981, 500, 1):
+        assert (R.denoiser_forward(d32, x, t, con, emo, sty) - _t(g[f"eps_t{t}_f32"])).abs().max() < 1e-5
+        e64 = R.denoiser_forward(d64, x.double(), t, con.double(), emo.double(), sty.double())
+        assert (e64 - _t(g[f"eps_t{t}_f64"])).abs().max() < 1e-12
+    e = R.denoiser_forward(d64, x.double(), 981, con.double(), None, None)
+    assert (e - _t(g["eps_t981_noemo_nosty_f64"])).abs().max() < 1e-12
+    e = R.denoiser_forward(d64, x.double(), 981, con.double(), emo.double(), None)
+    assert (e - _t(g["eps_t981_nosty_f64"])).abs().max() < 1e-12
+
+
+@pytest.mark.parametrize("name", ["ddim50_b4", "ddim1_b1", "ddim50_b1"])
+def test_ddim_golden(golden_dir, sds, name):
+    d32, _, d64, _ = sds
+    g = np.load(golden_dir / f"{name}.npz")
+    n = int(g["n_steps"])
+    a = [_t(g[k]) for k in ("latents0", "con", "emo", "sty")]
+    z64 = R.sample_latents(d64, *[t.double() for t in a], n, "ddim")
+    assert (z64 - _t(g["z_f64"])).abs().max() < 1e-10
+    z32 = R.sample_latents(d32, *a, n, "ddim")
+    assert (z32 - _t(g["z_f32"])).abs().max() < 2e-4
+
+
+def test_ddpm_golden(golden_dir, sds):
+    _, _, d64, _ = sds
+    g = np.load(golden_dir / "ddpm100_b2.npz")
+    n, B = int(g["n_steps"]), 2
+    noise = torch.randn(n, B, 128, generator=torch.Generator().manual_seed(int(g["noise_seed"])))
+    a = [_t(g[k]).double() for k in ("latents0", "con", "emo", "sty")]
+    z64 = R.sample_latents(d64, *a, n, "ddpm", noise.double())
+    assert (z64 - _t(g["z_f64"])).abs().max() < 1e-9
+
+
+def test_decode_and_rot_golden(golden_dir, sds):
+    _, v32, _, v64 = sds
+    g = np.load(golden_dir / "decode_b2.npz")
+    idx = g["frame_idx"]
+    f64 = R.vae_decode(v64, _t(g["z"]).double())
+    assert (f64[:, idx] - _t(g["feats_f64"])).abs().max() < 1e-11
+    f32 = R.vae_decode(v32, _t(g["z"]))
+    assert (f32[:, idx] - _t(g["feats_f32"])).abs().max() < 2e-5
+    m = R.feats_to_motion(f64)
+    assert R.geodesic_deg(m["poses"][:, idx], _t(g["poses_f64"])).max() < 1e-4   # acos near 1: ~1e-6 deg is rounding noise
+    c = np.load(golden_dir / "rot6d_cases.npz")
+    aa = R.rot6d_to_axis_angle(_t(c["d6"]).double())
+    assert R.geodesic_deg(aa, _t(c["aa_f64"])).max() < 1e-4
+    assert torch.allclose(R.rot6d_to_axis_angle(_t(c["d6"])), _t(c["aa_f32"]), atol=1e-5)
+
+
+def test_scheduler_tables():
+    assert R.ddim_timesteps(50)[:3] == [981, 961, 941] and R.ddim_timesteps(50)[-1] == 1
+    assert R.ddim_timesteps(1) == [1]
+    with pytest.raises(IndexError):
+        R.ddim_timesteps(1000)                       # alphas_cumprod[1000] -- invalid in the reference too
+    assert R.ddpm_timesteps(1000)[0] == 999 and R.ddpm_timesteps(1000)[-1] == 0
+    c = R.ddpm_coeffs(1000)["coef"]
+    assert c[-1, 4] == 0 and (c[:-1, 4] > 0).all()   # no noise at t = 0
+    ac = R.alphas_cumprod()
+    assert abs(float(ac[0]) - (1 - 0.00085)) < 1e-6 and float(ac[-1]) < 0.01
+    # DDIM eta=0 is deterministic: direction coefficient is sqrt(1 - a')
+    d = R.ddim_coeffs(50)["coef"]
+    assert torch.allclose(d[:, 2] ** 2 + d[:, 3] ** 2, torch.ones(50), atol=1e-6)
+
+
+@pytest.mark.skipif(not L.available(), reason="/root/reference not present (GPU box)")
+def test_restatement_matches_reference_modules(sds):
+    d32, v32, _, _ = sds
+    den, vae, tf = L.load_denoiser(d32), L.load_motionprior(v32), L.load_transforms()
+    g = torch.Generator().manual_seed(5)
+    B = 3
+    x, con, emo, sty = (torch.randn(B, n, generator=g) for n in (128, 256, 256, 256))
+    with torch.no_grad():
+        for t, e, s in ((981, emo, sty), (1, emo, None), (500, None, None)):
+            u = lambda z: None if z is None else z[:, None, :]
+            ref = den(sample=x[:, None, :], timestep=torch.tensor(t), con_hidden=u(con), emo_hidden=u(e),
+                      sty_hidden=u(s), lengths=[300] * B)[0][:, 0, :]
+            assert (R.denoiser_forward(d32, x, t, con, e, s) - ref).abs().max() < 1e-5
+        z = torch.randn(2, 128, generator=g)
+        ref = vae.decode(z[None], [300, 300])
+        assert (R.vae_decode(v32, z) - ref).abs().max() < 2e-5
+        d6 = ref[:, :, :-3].reshape(2, 300, 55, 6)
+        assert torch.equal(R.rot6d_to_axis_angle(d6), tf.matrix_to_axis_angle(tf.rotation_6d_to_matrix(d6)))
