@@ -284,52 +284,55 @@ int pack_denoiser(amuse_ctx* ctx, cudaStream_t st) {
       if (int rc = need(ctx, s + ".weight", {128, 256}, &skw)) return rc;
       if (int rc = need(ctx, s + ".bias", {128}, &skb)) return rc;
     }
-    for (int rank = 0; rank < kCluster; ++rank) {
+    // Tiles are K-major and k-pair interleaved for the FFMA2 micro-kernel:
+    //   element (k, n) of an [K][NCOL] tile lives at ((k >> 1) * NCOL + n) * 2 + (k & 1).
+    auto at = [](float* t, int ncol, int k, int n) -> float& { return t[((k >> 1) * ncol + n) * 2 + (k & 1)]; };
+    for (int rank = 0; rank < kCluster; ++rank) {   // rank == attention head owned by the CTA
       float* base = blob.data() + static_cast<size_t>(rank) * kBlobRankFloats;
-      const int head = rank >> 1;
+      const int head = rank;
       int off, n;
       const int t0 = (l < 5) ? 4 * l : 20 + 5 * (l - 5) + 1;   // index of this layer's QKV tile
-      if (l >= 5) {   // skip tile: Wt[k][c] = W[16*rank + c][k]
+      if (l >= 5) {   // skip tile, K-split: W(kk, c) = Wsk[c][64*rank + kk]; + full bias
         tile_info(t0 - 1, off, n);
         float* t = base + off;
-        for (int k = 0; k < 256; ++k)
-          for (int c = 0; c < 16; ++c) t[k * 16 + c] = skw->data[static_cast<size_t>(rank * 16 + c) * 256 + k];
-        for (int c = 0; c < 16; ++c) t[256 * 16 + c] = skb->data[rank * 16 + c];
+        for (int kk = 0; kk < 64; ++kk)
+          for (int c = 0; c < 128; ++c) at(t, 128, kk, c) = skw->data[static_cast<size_t>(c) * 256 + rank * 64 + kk];
+        std::memcpy(t + 64 * 128, skb->data.data(), 128 * 4);
       }
       {   // QKV tile of head `head`: local col j -> in_proj row  (j/32)*128 + head*32 + j%32
         tile_info(t0, off, n);
         float* t = base + off;
         for (int j = 0; j < 96; ++j) {
           const int row = (j / 32) * 128 + head * 32 + (j % 32);
-          for (int k = 0; k < 128; ++k) t[k * 96 + j] = inw->data[static_cast<size_t>(row) * 128 + k];
+          for (int k = 0; k < 128; ++k) at(t, 96, k, j) = inw->data[static_cast<size_t>(row) * 128 + k];
           t[128 * 96 + j] = inb->data[row];
         }
       }
-      {   // out_proj columns of the head: Wt[kk][n] = Wo[n][head*32 + kk]; + bo + norm1
+      {   // out_proj columns of the head: W(kk, n) = Wo[n][head*32 + kk]; + bo + norm1
         tile_info(t0 + 1, off, n);
         float* t = base + off;
         for (int kk = 0; kk < 32; ++kk)
-          for (int c = 0; c < 128; ++c) t[kk * 128 + c] = ow->data[static_cast<size_t>(c) * 128 + head * 32 + kk];
+          for (int c = 0; c < 128; ++c) at(t, 128, kk, c) = ow->data[static_cast<size_t>(c) * 128 + head * 32 + kk];
         std::memcpy(t + 32 * 128, ob->data.data(), 128 * 4);
         std::memcpy(t + 32 * 128 + 128, n1w->data.data(), 128 * 4);
         std::memcpy(t + 32 * 128 + 256, n1b->data.data(), 128 * 4);
       }
-      {   // linear1 rows [64*rank, +64): Wt[k][j]
+      {   // linear1 rows [128*rank, +128): W(k, j) = W1[128*rank + j][k]
         tile_info(t0 + 2, off, n);
         float* t = base + off;
-        for (int j = 0; j < 64; ++j) {
-          for (int k = 0; k < 128; ++k) t[k * 64 + j] = w1->data[static_cast<size_t>(rank * 64 + j) * 128 + k];
-          t[128 * 64 + j] = b1->data[rank * 64 + j];
+        for (int j = 0; j < 128; ++j) {
+          for (int k = 0; k < 128; ++k) at(t, 128, k, j) = w1->data[static_cast<size_t>(rank * 128 + j) * 128 + k];
+          t[128 * 128 + j] = b1->data[rank * 128 + j];
         }
       }
-      {   // linear2 columns [64*rank, +64): Wt[kk][n] = W2[n][64*rank + kk]; + b2 + norm2
+      {   // linear2 columns [128*rank, +128): W(kk, n) = W2[n][128*rank + kk]; + b2 + norm2
         tile_info(t0 + 3, off, n);
         float* t = base + off;
-        for (int kk = 0; kk < 64; ++kk)
-          for (int c = 0; c < 128; ++c) t[kk * 128 + c] = w2->data[static_cast<size_t>(c) * 512 + rank * 64 + kk];
-        std::memcpy(t + 64 * 128, b2->data.data(), 128 * 4);
-        std::memcpy(t + 64 * 128 + 128, n2w->data.data(), 128 * 4);
-        std::memcpy(t + 64 * 128 + 256, n2b->data.data(), 128 * 4);
+        for (int kk = 0; kk < 128; ++kk)
+          for (int c = 0; c < 128; ++c) at(t, 128, kk, c) = w2->data[static_cast<size_t>(c) * 512 + rank * 128 + kk];
+        std::memcpy(t + 128 * 128, b2->data.data(), 128 * 4);
+        std::memcpy(t + 128 * 128 + 128, n2w->data.data(), 128 * 4);
+        std::memcpy(t + 128 * 128 + 256, n2b->data.data(), 128 * 4);
       }
     }
   }
@@ -487,11 +490,8 @@ bool any_with_prefix(amuse_ctx* ctx, const char* pre) {
   return false;
 }
 
-int choose_S(int B) {   // clips per 8-CTA cluster: fill ~16 clusters (128 SMs) first, then up to 4 clips each
-  int S = (B + 15) / 16;
-  if (S < 1) S = 1;
-  if (S > dn::kSMax) S = dn::kSMax;
-  return S;
+int choose_S(int B) {   // clips per 4-CTA cluster: one clip per cluster while all clusters stay co-resident
+  return (B <= dn::kMaxClusters) ? 1 : dn::kSMax;
 }
 
 int run_denoise(amuse_ctx* ctx, int B, Schedule& sc, int clip, const float* latents0, const float* z_con,

@@ -6,23 +6,26 @@
 namespace amuse {
 namespace dn {
 
-constexpr int kCluster = 8;            // CTAs per thread-block cluster (one cluster = up to kSMax clips)
+constexpr int kCluster = 4;            // CTAs per thread-block cluster = attention heads (one head per CTA)
 constexpr int kThreads = 256;
-constexpr int kSMax = 4;               // clips per cluster
+constexpr int kSMax = 2;               // clips per cluster
 constexpr int kTMax = 5;               // tokens per clip: z, t, con, emo, sty (denoiser.py:174,180)
 constexpr int kRMax = kSMax * kTMax;   // activation rows per cluster
 constexpr int kTilesPerStep = 40;      // 9 layers x 4 weight tiles + 4 skip-linear tiles
+constexpr int kMaxClusters = 33;       // co-resident 4-CTA clusters with ~225 KB smem on B200 (measured,
+                                       // scripts/occ_probe.cu: cudaOccupancyMaxActiveClusters = 33)
 
 // Per-CTA-rank weight stream ("blob"): the tiles one CTA consumes during one denoiser
 // evaluation, in consumption order, each tile K-major ([k][n_local]) followed by the
 // bias / LayerNorm vectors its epilogue needs.  Sizes in floats.
-constexpr int kTileQKV = 128 * 96 + 96;          // in_proj rows of one head: q|k|v 32 each  + bias
-constexpr int kTileWO = 32 * 128 + 128 + 256;    // out_proj columns of one head (K-split)   + bias + norm1
-constexpr int kTileW1 = 128 * 64 + 64;           // linear1 rows [64*rank, +64)              + bias
-constexpr int kTileW2 = 64 * 128 + 128 + 256;    // linear2 columns [64*rank, +64) (K-split) + bias + norm2
-constexpr int kTileSK = 256 * 16 + 16;           // linear_blocks rows [16*rank, +16)        + bias
+constexpr int kTileQKV = 128 * 96 + 96;          // in_proj rows of head `rank`: q|k|v 32 each   + bias
+constexpr int kTileWO = 32 * 128 + 128 + 256;    // out_proj columns of head `rank` (K-split)    + bias + norm1
+constexpr int kTileW1 = 128 * 128 + 128;         // linear1 rows [128*rank, +128)                + bias
+constexpr int kTileW2 = 128 * 128 + 128 + 256;   // linear2 columns [128*rank, +128) (K-split)   + bias + norm2
+constexpr int kTileSK = 64 * 128 + 128;          // linear_blocks columns [64*rank, +64) (K-split) + bias
 constexpr int kLayerFloats = kTileQKV + kTileWO + kTileW1 + kTileW2;
 constexpr int kBlobRankFloats = 9 * kLayerFloats + 4 * kTileSK;
+constexpr int kTileMax = kTileW2;
 
 __host__ __device__ inline void tile_info(int i, int& off, int& n) {
   // i in [0, 40): layers 0..4 have 4 tiles, layers 5..8 have 5 (skip-linear first)

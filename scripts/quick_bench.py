@@ -50,16 +50,16 @@ def main():
     eng.profile_arm(3)
     eng.denoise(l0, con, emo, sty, n_steps=8)
     st = eng.profile_read(96)
-    names = ["skip", "qkv", "attn", "oproj+sync1", "red+sync2", "ln1", "ffn1", "ffn2+sync3", "red+sync4", "ln2"]
+    names = ["skip", "qkv", "attn", "oproj+sync", "sum+ln1", "ffn1", "ffn2+sync", "sum+ln2"]
     print("step cycles total:", st[92] - st[0], " build-x:", st[1] - st[0])
     for l in range(9):
         base = 2 + l * 10
-        prev = st[1] if l == 0 else st[2 + (l - 1) * 10 + 9]
+        prev = st[1] if l == 0 else st[2 + (l - 1) * 10 + 7]
         row = []
-        for j in range(10):
+        for j in range(8):
             row.append(st[base + j] - (prev if j == 0 else st[base + j - 1]))
         print(f"layer {l}: " + " ".join(f"{n}={c}" for n, c in zip(names, row)))
-    print("final+update:", st[92] - st[2 + 8 * 10 + 9])
+    print("final+update:", st[92] - st[2 + 8 * 10 + 7])
 
 
 if __name__ == "__main__":
