@@ -284,9 +284,16 @@ int pack_denoiser(amuse_ctx* ctx, cudaStream_t st) {
       if (int rc = need(ctx, s + ".weight", {128, 256}, &skw)) return rc;
       if (int rc = need(ctx, s + ".bias", {128}, &skb)) return rc;
     }
-    // Tiles are K-major and k-pair interleaved for the FFMA2 micro-kernel:
-    //   element (k, n) of an [K][NCOL] tile lives at ((k >> 1) * NCOL + n) * 2 + (k & 1).
-    auto at = [](float* t, int ncol, int k, int n) -> float& { return t[((k >> 1) * ncol + n) * 2 + (k & 1)]; };
+    // Tiles are K-major and k-pair interleaved for the FFMA2 micro-kernel: element (k, p) of a
+    // [K][NCOL] tile lives at ((k >> 1) * NCOL + p) * 2 + (k & 1).  For the 128-wide tiles the LDS.64
+    // a lane issues at positions lane + 32*j (j = 0..3) must hand it the output columns
+    // {2*lane, 2*lane+1, 64+2*lane, 64+2*lane+1}: logical column c sits at
+    //   p = (c < 64) ? (c & 1) * 32 + c / 2  :  (2 + (c & 1)) * 32 + (c - 64) / 2.
+    auto at = [](float* t, int ncol, int k, int c) -> float& {
+      int p = c;
+      if (ncol == 128) p = (c < 64) ? ((c & 1) * 32 + (c >> 1)) : ((2 + (c & 1)) * 32 + ((c - 64) >> 1));
+      return t[((k >> 1) * ncol + p) * 2 + (k & 1)];
+    };
     for (int rank = 0; rank < kCluster; ++rank) {   // rank == attention head owned by the CTA
       float* base = blob.data() + static_cast<size_t>(rank) * kBlobRankFloats;
       const int head = rank;
@@ -322,7 +329,7 @@ int pack_denoiser(amuse_ctx* ctx, cudaStream_t st) {
         float* t = base + off;
         for (int j = 0; j < 128; ++j) {
           for (int k = 0; k < 128; ++k) at(t, 128, k, j) = w1->data[static_cast<size_t>(rank * 128 + j) * 128 + k];
-          t[128 * 128 + j] = b1->data[rank * 128 + j];
+          t[128 * 128 + j] = b1->data[rank * 128 + j];   // tail: bias | (no LayerNorm: zeros)
         }
       }
       {   // linear2 columns [128*rank, +128): W(kk, n) = W2[n][128*rank + kk]; + b2 + norm2

@@ -43,15 +43,16 @@ constexpr int kWBufFloats = 16768;   // == kTileW2 (largest tile), multiple of 3
 static_assert(kWBufFloats >= kTileMax && kWBufFloats % 32 == 0, "weight ring slot too small");
 constexpr int kQkvLd = 100;          // q|k|v row stride: 16-B aligned rows, conflict-free T x T dot products
 constexpr int kOhLd = 36;            // attention-output row stride (16-B aligned rows)
-constexpr int kRedFloats = 7 * 5 * 128;   // K-split partial sums: (KSPLIT-1) x rows x 128
+constexpr int kRedFloats = 8 * 5 * 128;      // K-split partial sums: KSPLIT x rows x 128  (= 4 x 10 x 128)
 constexpr int kPsFloats = 3 * kRMax * 128;   // partial sums received from the 3 peer CTAs
+constexpr int kQkvOhFloats = kRMax * kQkvLd + kRMax * kOhLd;
+static_assert(kQkvOhFloats >= kRMax * 128, "Hs aliases the q|k|v + attention-output region");
 
 // ---------------------------------------------------------------- shared-memory carve-up
 // Offsets (floats) from the dynamic shared-memory base.  Every pointer is formed as
 // `smem + constant`, so the compiler keeps the .shared address space (LDS/STS, not generic LD/ST).
-constexpr int kActFloats = kRMax * 128 + 4 * kRMax * 128 + 2 * kPsFloats + kRMax * kQkvLd + kRMax * kOhLd +
-                           kRMax * 128 + kRedFloats + kSMax * 3 * 128 + 256 + kSMax * 128 + kSMax * 128 + 128 + 256 +
-                           96 + 128 + 256 + 128 + 128 + 256 + 128;
+constexpr int kActFloats = kRMax * 128 + 4 * kRMax * 128 + 2 * kPsFloats + kQkvOhFloats + kRedFloats +
+                           kSMax * 3 * 128 + 256 + kSMax * 128 + kSMax * 128 + 128 + 256 + 96 + kTileTail;
 constexpr int kSmemFloats = 2 * kWBufFloats + kActFloats + 16 /*mbarriers + pad*/;
 static_assert(kSmemFloats * 4 <= 232448, "exceeds the 227 KB shared-memory limit of sm_100");
 
@@ -64,22 +65,18 @@ struct Smem {
   static constexpr int oPs = oSK + 4 * kRMax * 128;          // [2][3][10][128] peer partials (remote-written)
   static constexpr int oQKV = oPs + 2 * kPsFloats;           // [10][100] q|k|v of my head
   static constexpr int oOh = oQKV + kRMax * kQkvLd;          // [10][36] attention output of my head
-  static constexpr int oHs = oOh + kRMax * kOhLd;            // [10][128] my 128 hidden units
-  static constexpr int oRED = oHs + kRMax * 128;             // K-split partial sums
+  static constexpr int oHs = oQKV;                           // [10][128] my 128 hidden units -- ALIASES q|k|v/Oh
+                                                             // (dead between out_proj and the next layer's QKV)
+  static constexpr int oRED = oQKV + kQkvOhFloats;           // K-split partial sums
   static constexpr int oCs = oRED + kRedFloats;              // [2][3][128] condition tokens (+PE)
   static constexpr int oPe = oCs + kSMax * 3 * 128;          // [2][128]
   static constexpr int oZs = oPe + 256;                      // [2][128] current latents
   static constexpr int oEs = oZs + kSMax * 128;              // [2][128] eps
   static constexpr int oTemb = oEs + kSMax * 128;            // [128]
   static constexpr int oFn = oTemb + 128;                    // [256] final norm
-  static constexpr int oBqkv = oFn + 256;                    // [96]
-  static constexpr int oBo = oBqkv + 96;                     // [128]
-  static constexpr int oLn1 = oBo + 128;                     // [256]
-  static constexpr int oB1 = oLn1 + 256;                     // [128]
-  static constexpr int oB2 = oB1 + 128;                      // [128]
-  static constexpr int oLn2 = oB2 + 128;                     // [256]
-  static constexpr int oBsk = oLn2 + 256;                    // [128]
-  static constexpr int oBar = oBsk + 128;                    // 4 mbarriers: 2 weight ring, 2 exchange
+  static constexpr int oBqkv = oFn + 256;                    // [96]  q|k|v bias of the current layer
+  static constexpr int oTail = oBqkv + 96;                   // [384] bias | LN weight | LN bias of the current stage
+  static constexpr int oBar = oTail + kTileTail;             // 4 mbarriers: 2 weight ring, 2 exchange
   static_assert(oBar == kActFloats, "carve-up does not match kActFloats");
   __device__ __forceinline__ uint64_t* wbar(uint32_t i) const { return reinterpret_cast<uint64_t*>(at(oBar)) + i; }
   __device__ __forceinline__ uint64_t* xbar(uint32_t i) const { return reinterpret_cast<uint64_t*>(at(oBar)) + 2 + i; }
@@ -105,76 +102,56 @@ __device__ __forceinline__ const float* wp_acquire(const Smem& s, const WPipe& w
   return s.wbuf(w.g & 1);
 }
 // Call after a __syncthreads() that follows the last read of tile g: hands the buffer back
-// to the TMA engine for tile g+2.
+// to the TMA engine for tile g+2.  Issued by one lane of warp 7 -- the warp with the least
+// epilogue work -- so that the ~0.5k-cycle issue latency stays off the critical path (measured:
+// with thread 0 issuing, warp 0's epilogue was 700 cycles late in every stage).  No proxy fence:
+// the buffer was only READ by this CTA and every reader has passed the barrier.
+constexpr int kIssuerTid = 7 * 32;
 __device__ __forceinline__ void wp_release(const Smem& s, WPipe& w, int tid) {
-  if (tid == 0 && w.g + 2 < w.total) {
-    fence_proxy_async();
-    wp_issue(s, w, w.g + 2);
-  }
+  if (tid == kIssuerTid && w.g + 2 < w.total) wp_issue(s, w, w.g + 2);
   ++w.g;
 }
 
-// ---------------------------------------------------------------- warp roles
-// 8 warps = RB row-blocks (5 rows each) x KSPLIT = 8/RB K-slices.  The warp that folds the
-// K-split partials of row-block rb (and runs its epilogue / LayerNorm) is the one with
-// ks == rb, so the folding warps sit on different SM sub-partitions (warp % 4).
-template <int RB>
-struct Role {
-  static constexpr int KS = 8 / RB;
-  int rb, ks;
-  bool fold;
-  int slot;   // parking slot of a non-folding warp: 0 .. KS-2
-  __device__ __forceinline__ explicit Role(int warp) {
-    rb = warp / KS;
-    ks = warp % KS;
-    fold = (ks == rb);
-    slot = (ks - rb - 1 + KS) % KS;
-  }
-};
-
 // ---------------------------------------------------------------- 5-row FFMA2 micro-kernel
 // acc[i][j] = sum_{k in my K slice} A[rb*5+i][k] * W[k][col(lane,j)]
-// Blackwell issues a 3-register FFMA at half rate; the packed FFMA2 (fma.rn.f32x2, two fp32 FMAs
-// on 64-bit register pairs) is what reaches 128 FMA/clk/SM.  The two lanes of an FFMA2 are two
-// consecutive k: weight tiles are stored k-pair interleaved, Wt2[k/2][n][2], so one 64-bit
-// word holds (W[k][n], W[k+1][n]); an A-row float4 supplies (A[k],A[k+1]) and (A[k+2],A[k+3]).
-// Even-k and odd-k products accumulate in the two halves and are added at the end.
-//   CONTIG (TC == 4): lane owns columns 4*lane .. 4*lane+3   (NCOL = 128, two LDS.128 per k-pair)
-//   strided         : lane owns columns lane + 32*j           (NCOL = 32*TC, one LDS.64 per column)
-// A-row loads are warp-uniform 128-bit broadcasts; weight loads are conflict-free.
-template <int NCOL, int KDIM, int TC, int KSPLIT, bool CONTIG>
-__device__ __forceinline__ void gemm5(const float* __restrict__ A, int lda, const float* __restrict__ Wt2, int rb,
-                                      int ks, int lane, float (&acc)[5][TC]) {
-  constexpr int KPER = KDIM / KSPLIT;
-  static_assert(KPER % 4 == 0, "K slice must be a multiple of 4");
-  static_assert(!CONTIG || TC == 4, "contiguous mapping owns 4 columns per lane");
+//
+// Measured on B200 (scripts/ubench.cu): a 3-register FFMA issues every 1.44 cycles per SM
+// sub-partition and the packed FFMA2 (two fp32 FMAs on 64-bit register pairs) every 2.75, i.e. both
+// top out near 90 FMA/clk/SM, but FFMA2 halves the issue slots; LDS.64 sustains 125 B/clk/SM while
+// LDS.128 only 64 B/clk, and a warp-uniform LDS.128 costs 2.2 cycles.  Hence:
+//   * the two halves of an FFMA2 are two consecutive k: weight tiles are stored k-pair interleaved,
+//     Wt2[k/2][p][2], so one 64-bit word holds (W[k][c], W[k+1][c]); an A-row float4 supplies
+//     (A[k],A[k+1]) and (A[k+2],A[k+3]).  Even- and odd-k products accumulate in the two halves;
+//   * weights are read with LDS.64 only: lane reads tile positions p = lane + 32*j.  For the
+//     128-wide tiles the host packs the tile so that lane owns the output columns
+//     {2*lane, 2*lane+1, 64+2*lane, 64+2*lane+1} (j = 0..3): every epilogue access (K-split park /
+//     gather, bias, residual, LayerNorm params, DSMEM stores) is then a conflict-free 64-bit access
+//     too;  for the q|k|v tile position p is the natural (q,k,v)[lane] triple;
+//   * A-row loads are warp-uniform 128-bit broadcasts.
+// ITERS 4-k iterations starting at a0 = A + (row block, my K slice) / w = Wt2 + my K slice.  Fully
+// unrolled: with a runtime trip count (or unroll 2) the loads are not hoisted far enough ahead of
+// the FFMA2s and every GEMM stage got 15-25% slower (measured), which outweighs the extra
+// instruction-cache pressure of the larger body.
+template <int NCOL, int TC, int ITERS>
+__device__ __forceinline__ void gemm5(const float* __restrict__ a0, int lda, const float* __restrict__ w,
+                                      float (&acc)[5][TC]) {
+  static_assert(NCOL == 32 * TC, "lane owns tile positions lane + 32*j");
   float2 acc2[5][TC];
 #pragma unroll
   for (int i = 0; i < 5; ++i)
 #pragma unroll
     for (int j = 0; j < TC; ++j) acc2[i][j] = make_float2(0.f, 0.f);
-  const float* a0 = A + (rb * 5) * lda + ks * KPER;
-  const float* w = Wt2 + (ks * (KPER / 2)) * (NCOL * 2) + (CONTIG ? lane * 8 : lane * 2);
 #pragma unroll
-  for (int kk = 0; kk < KPER; kk += 4) {
+  for (int it = 0; it < ITERS; ++it) {
     float4 a[5];
 #pragma unroll
-    for (int i = 0; i < 5; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + i * lda + kk);
+    for (int i = 0; i < 5; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + i * lda + it * 4);
 #pragma unroll
     for (int kp = 0; kp < 2; ++kp) {
       float2 wv[TC];
-      const float* wr = w + (kk / 2 + kp) * (NCOL * 2);
-      if (CONTIG) {
-        const float4 t0 = *reinterpret_cast<const float4*>(wr);
-        const float4 t1 = *reinterpret_cast<const float4*>(wr + 4);
-        wv[0] = make_float2(t0.x, t0.y);
-        wv[1] = make_float2(t0.z, t0.w);
-        wv[2] = make_float2(t1.x, t1.y);
-        wv[3] = make_float2(t1.z, t1.w);
-      } else {
+      const float* wr = w + (it * 2 + kp) * (NCOL * 2);
 #pragma unroll
-        for (int j = 0; j < TC; ++j) wv[j] = *reinterpret_cast<const float2*>(wr + 64 * j);
-      }
+      for (int j = 0; j < TC; ++j) wv[j] = *reinterpret_cast<const float2*>(wr + 64 * j);
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
         const float2 av = (kp == 0) ? make_float2(a[i].x, a[i].y) : make_float2(a[i].z, a[i].w);
@@ -189,140 +166,116 @@ __device__ __forceinline__ void gemm5(const float* __restrict__ A, int lda, cons
     for (int j = 0; j < TC; ++j) acc[i][j] = acc2[i][j].x + acc2[i][j].y;
 }
 
-// K-split reduction through shared memory: non-folding warps park their partials ...
-template <int NCOL, int TC, bool CONTIG, int RB>
-__device__ __forceinline__ void park(float* RED, const Role<RB>& r, int lane, const float (&acc)[5][TC]) {
-  if (r.fold) return;
-  float* dst = RED + ((r.slot * RB + r.rb) * 5) * NCOL;
+// K-split reduction through shared memory.  Every warp parks its partial tile in
+// RED[ks][row][NCOL]; after a __syncthreads() the row-owner warps (warp w owns rows w and w+8)
+// add the KSPLIT partials of their rows, so the epilogues run on all 8 warps.
+// A lane's 4 columns as two float2: lo = columns (2*lane, 2*lane+1), hi = (64+2*lane, 64+2*lane+1).
+struct Row4 {
+  float2 lo, hi;
+};
+__device__ __forceinline__ Row4 ld_row4(const float* row, int lane) {
+  Row4 r;
+  r.lo = *reinterpret_cast<const float2*>(row + 2 * lane);
+  r.hi = *reinterpret_cast<const float2*>(row + 64 + 2 * lane);
+  return r;
+}
+__device__ __forceinline__ void st_row4(float* row, int lane, const Row4& v) {
+  *reinterpret_cast<float2*>(row + 2 * lane) = v.lo;
+  *reinterpret_cast<float2*>(row + 64 + 2 * lane) = v.hi;
+}
+__device__ __forceinline__ Row4 add4(const Row4& a, const Row4& b) {
+  Row4 r;
+  r.lo = make_float2(a.lo.x + b.lo.x, a.lo.y + b.lo.y);
+  r.hi = make_float2(a.hi.x + b.hi.x, a.hi.y + b.hi.y);
+  return r;
+}
+template <int RT>
+__device__ __forceinline__ void park4(float* RED, int rb, int ks, int lane, const float (&acc)[5][4]) {
+  float* dst = RED + ((ks * RT + rb * 5) * 128);
 #pragma unroll
   for (int i = 0; i < 5; ++i) {
-    if (CONTIG) {
-      *reinterpret_cast<float4*>(dst + i * NCOL + lane * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < TC; ++j) dst[i * NCOL + lane + 32 * j] = acc[i][j];
-    }
+    Row4 v;
+    v.lo = make_float2(acc[i][0], acc[i][1]);
+    v.hi = make_float2(acc[i][2], acc[i][3]);
+    st_row4(dst + i * 128, lane, v);
   }
 }
-// ... and after a __syncthreads() the folding warp of each row-block adds them up.
-template <int NCOL, int TC, bool CONTIG, int RB>
-__device__ __forceinline__ void fold(const float* RED, const Role<RB>& r, int lane, float (&acc)[5][TC]) {
+template <int RT, int KS>
+__device__ __forceinline__ Row4 gather4(const float* RED, int row, int lane) {
+  Row4 v = ld_row4(RED + row * 128, lane);
 #pragma unroll
-  for (int q = 0; q < Role<RB>::KS - 1; ++q) {
-    const float* src = RED + ((q * RB + r.rb) * 5) * NCOL;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      if (CONTIG) {
-        const float4 t = *reinterpret_cast<const float4*>(src + i * NCOL + lane * 4);
-        acc[i][0] += t.x;
-        acc[i][1] += t.y;
-        acc[i][2] += t.z;
-        acc[i][3] += t.w;
-      } else {
-#pragma unroll
-        for (int j = 0; j < TC; ++j) acc[i][j] += src[i * NCOL + lane + 32 * j];
-      }
-    }
-  }
+  for (int q = 1; q < KS; ++q) v = add4(v, ld_row4(RED + (q * RT + row) * 128, lane));
+  return v;
 }
 
-// Exchange of K-split partial sums across the cluster, without a barrier: the folding warp stores
-// its full-width partial (5 rows x 4 columns per lane) straight into the 3 peers' receive buffers
-// with st.async, which credits the bytes to the PEER'S mbarrier (complete_tx).  Each CTA arms its
-// own mbarrier with the byte count it expects and waits on it.  Receive buffers / mbarriers
-// alternate with the running exchange index xe (buffer = xe & 1): a peer can only start exchange
-// xe+2 (same buffer) after it completed xe+1, which needs MY xe+1 data, which I send after I have
-// consumed xe -- so a buffer is never overwritten before it has been read, and phases never mix.
-__device__ __forceinline__ void st_async_f4(uint32_t dst, float4 v, uint32_t mbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
-               ::"r"(dst), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)),
-               "r"(__float_as_uint(v.w)), "r"(mbar)
+// ---------------------------------------------------------------- DSMEM exchange
+// Exchange of K-split partial sums across the cluster, without a barrier: a row-owner warp stores
+// its row of the CTA's full-width partial straight into the 3 peers' receive buffers with st.async,
+// which credits the bytes to the PEER'S mbarrier (complete_tx).  Each CTA arms its own mbarrier with
+// the byte count it expects and waits on it.  Receive buffers / mbarriers alternate with the
+// running exchange index xe (buffer = xe & 1): a peer can only start exchange xe+2 (same buffer)
+// after it completed xe+1, which needs MY xe+1 data, which I send after I have consumed xe -- so a
+// buffer is never overwritten before it has been read, and phases never mix.
+__device__ __forceinline__ void st_async_f2(uint32_t dst, float2 v, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(dst),
+               "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(mbar)
                : "memory");
 }
-__device__ __forceinline__ void broadcast_partial(const Smem& s, uint32_t xe, uint32_t rank, int rb, int lane,
-                                                  const float (&acc)[5][4]) {
+__device__ __forceinline__ void send_row(const Smem& s, uint32_t xe, uint32_t rank, int row, int lane, const Row4& v) {
   float* ps = s.Ps(xe & 1);
   uint64_t* bar = s.xbar(xe & 1);
 #pragma unroll
   for (uint32_t d = 1; d < kCluster; ++d) {
     const uint32_t peer = (rank + d) & (kCluster - 1);
     const uint32_t slot = (rank < peer) ? rank : rank - 1;   // my slot in the peer's [3][rows][128] buffer
-    const uint32_t base = map_to_rank(ps + (slot * kRMax + rb * 5) * 128 + lane * 4, peer);
+    const uint32_t dst = map_to_rank(ps + (slot * kRMax + row) * 128 + 2 * lane, peer);
     const uint32_t rbar = map_to_rank(bar, peer);
-#pragma unroll
-    for (int i = 0; i < 5; ++i)
-      st_async_f4(base + i * 128 * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]), rbar);
+    st_async_f2(dst, v.lo, rbar);
+    st_async_f2(dst + 64 * 4, v.hi, rbar);
   }
 }
-template <int RB>
+template <int RT>
 __device__ __forceinline__ void exchange_arm(const Smem& s, uint32_t xe, int tid) {
-  if (tid == 0) mbar_arrive_expect_tx(s.xbar(xe & 1), 3u * RB * 5u * 128u * 4u);
+  if (tid == kIssuerTid) mbar_arrive_expect_tx(s.xbar(xe & 1), 3u * RT * 128u * 4u);
 }
 __device__ __forceinline__ void exchange_wait(const Smem& s, uint32_t xe) {
   mbar_wait(s.xbar(xe & 1), (xe >> 1) & 1);
 }
+__device__ __forceinline__ Row4 add_peers(const float* Ps, int row, int lane, Row4 v) {
+#pragma unroll
+  for (int q = 0; q < 3; ++q) v = add4(v, ld_row4(Ps + (q * kRMax + row) * 128, lane));
+  return v;
+}
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
-// acc (my partial) + 3 peer partials + bias [+ residual] -> optional LayerNorm -> dst rows.
-// One warp holds 5 full rows (32 lanes x 4 columns); the 5 LayerNorm chains are interleaved.
-template <bool RESIDUAL, bool LN>
-__device__ __forceinline__ void sum_norm_store(const float* Ps, const float* bias, const float* resid,
-                                               const float* lnp, float* dst, float* dst2, int rb, int lane,
-                                               float (&acc)[5][4]) {
-  const float4 b = *reinterpret_cast<const float4*>(bias + lane * 4);
-  float4 v[5];
+// LayerNorm of up to two 128-wide rows held 4 values per lane; the two chains are interleaved.
+__device__ __forceinline__ void layernorm2(Row4 (&v)[2], const float* lnp, int lane) {
+  const Row4 g = ld_row4(lnp, lane), be = ld_row4(lnp + 128, lane);
+  float s1[2], s2[2];
 #pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    v[i] = make_float4(acc[i][0] + b.x, acc[i][1] + b.y, acc[i][2] + b.z, acc[i][3] + b.w);
+  for (int i = 0; i < 2; ++i) s1[i] = (v[i].lo.x + v[i].lo.y) + (v[i].hi.x + v[i].hi.y);
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const float4 t = *reinterpret_cast<const float4*>(Ps + ((q * kRMax) + rb * 5 + i) * 128 + lane * 4);
-      v[i].x += t.x;
-      v[i].y += t.y;
-      v[i].z += t.z;
-      v[i].w += t.w;
-    }
-    if (RESIDUAL) {
-      const float4 x = *reinterpret_cast<const float4*>(resid + (rb * 5 + i) * 128 + lane * 4);
-      v[i].x += x.x;
-      v[i].y += x.y;
-      v[i].z += x.z;
-      v[i].w += x.w;
-    }
-  }
-  if (LN) {
-    const float4 g = *reinterpret_cast<const float4*>(lnp + lane * 4);
-    const float4 be = *reinterpret_cast<const float4*>(lnp + 128 + lane * 4);
-    float s1[5], s2[5];
+  for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-    for (int i = 0; i < 5; ++i) s1[i] = v[i].x + v[i].y + v[i].z + v[i].w;
+    for (int i = 0; i < 2; ++i) s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-      for (int i = 0; i < 5; ++i) s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      const float mean = s1[i] * (1.0f / 128.0f);
-      v[i].x -= mean;
-      v[i].y -= mean;
-      v[i].z -= mean;
-      v[i].w -= mean;
-      s2[i] = v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-      for (int i = 0; i < 5; ++i) s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      const float rstd = 1.0f / sqrtf(s2[i] * (1.0f / 128.0f) + kLnEps);
-      v[i] = make_float4(v[i].x * rstd * g.x + be.x, v[i].y * rstd * g.y + be.y, v[i].z * rstd * g.z + be.z,
-                         v[i].w * rstd * g.w + be.w);
-    }
+  for (int i = 0; i < 2; ++i) {
+    const float mean = s1[i] * (1.0f / 128.0f);
+    v[i].lo.x -= mean;
+    v[i].lo.y -= mean;
+    v[i].hi.x -= mean;
+    v[i].hi.y -= mean;
+    s2[i] = (v[i].lo.x * v[i].lo.x + v[i].lo.y * v[i].lo.y) + (v[i].hi.x * v[i].hi.x + v[i].hi.y * v[i].hi.y);
   }
 #pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    *reinterpret_cast<float4*>(dst + (rb * 5 + i) * 128 + lane * 4) = v[i];
-    if (dst2) *reinterpret_cast<float4*>(dst2 + (rb * 5 + i) * 128 + lane * 4) = v[i];
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float rstd = rsqrtf(s2[i] * (1.0f / 128.0f) + kLnEps);
+    v[i].lo = make_float2(v[i].lo.x * rstd * g.lo.x + be.lo.x, v[i].lo.y * rstd * g.lo.y + be.lo.y);
+    v[i].hi = make_float2(v[i].hi.x * rstd * g.hi.x + be.hi.x, v[i].hi.y * rstd * g.hi.y + be.hi.y);
   }
 }
 
@@ -338,10 +291,12 @@ __device__ __forceinline__ void copy_params(float* dst, const float* src, int n,
 }  // namespace
 
 // ================================================================= the kernel
+// RB = row blocks of 5 rows: 1 (one clip per cluster) or 2 (two clips).  8 warps = RB x KS.
 template <int RB>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     denoise_loop_kernel(const Params p) {
-  constexpr int KS = 8 / RB;
+  constexpr int KS = 8 / RB;      // K-split factor of every GEMM
+  constexpr int RT = RB * 5;      // activation rows computed by the GEMMs
   extern __shared__ __align__(128) float smem_raw[];
   Smem s;
   s.base = smem_raw;
@@ -358,17 +313,15 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   float* const tembs = s.at(Smem::oTemb);
   float* const fn = s.at(Smem::oFn);
   float* const par_bqkv = s.at(Smem::oBqkv);
-  float* const par_bo = s.at(Smem::oBo);
-  float* const par_ln1 = s.at(Smem::oLn1);
-  float* const par_b1 = s.at(Smem::oB1);
-  float* const par_b2 = s.at(Smem::oB2);
-  float* const par_ln2 = s.at(Smem::oLn2);
-  float* const par_bsk = s.at(Smem::oBsk);
+  float* const par_tail = s.at(Smem::oTail);   // bias | LN weight | LN bias of the stage in flight
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t rank = cluster_ctarank();   // == attention head owned by this CTA
   const int cid = static_cast<int>(cluster_id_x());
-  const Role<RB> role(warp);
+  const int rb = warp / KS, ks = warp % KS;  // GEMM role: row block, K slice
+  // reduce / epilogue role: warp w owns rows w and w + 8 (second one only when RT == 10 and w < 2)
+  const int row0 = warp, row1 = warp + 8;
+  const bool own0 = row0 < RT, own1 = row1 < RT;
   const int T = p.T;
   const int s_base = cid * p.S;
   const int S = min(p.S, p.B - s_base);      // clips of this cluster (>= 1 by grid construction)
@@ -420,6 +373,44 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   float noise_next = 0.f;
   if (!use_rng && owns_elem) noise_next = __ldg(p.step_noise + static_cast<size_t>(s_base) * 128 + tid);
 
+  // K-split partial -> st.async exchange -> sum + bias [+ residual] [+ LayerNorm] -> Xs [, skip stack].
+  // A lambda so that the three users (skip fusion, out_proj, FFN2) share one source form.
+  auto exchange_epilogue = [&](const float* bias, const float* resid, const float* lnp, float* dst2, int prof_slot,
+                               bool do_prof) {
+    if (own0) {
+      Row4 v[2];
+      v[0] = gather4<RT, KS>(RED, row0, lane);
+      send_row(s, xe, rank, row0, lane, v[0]);
+      v[1] = v[0];
+      if (own1) {
+        v[1] = gather4<RT, KS>(RED, row1, lane);
+        send_row(s, xe, rank, row1, lane, v[1]);
+      }
+      const Row4 b = ld_row4(bias, lane);
+      v[0] = add4(v[0], b);
+      if (resid) v[0] = add4(v[0], ld_row4(resid + row0 * 128, lane));
+      if (own1) {
+        v[1] = add4(v[1], b);
+        if (resid) v[1] = add4(v[1], ld_row4(resid + row1 * 128, lane));
+      }
+      if (prof_slot >= 0 && prof_slot < 12 && do_prof && tid == 0) p.prof[prof_slot + 100] = clock64();   // layer 0 only
+      exchange_wait(s, xe);
+      if (prof_slot >= 0 && do_prof && tid == 0) p.prof[prof_slot] = clock64();
+      const float* ps = s.Ps(xe & 1);
+      v[0] = add_peers(ps, row0, lane, v[0]);
+      if (own1) v[1] = add_peers(ps, row1, lane, v[1]);
+      if (lnp) layernorm2(v, lnp, lane);
+      st_row4(Xs + row0 * 128, lane, v[0]);
+      if (dst2) st_row4(dst2 + row0 * 128, lane, v[0]);
+      if (own1) {
+        st_row4(Xs + row1 * 128, lane, v[1]);
+        if (dst2) st_row4(dst2 + row1 * 128, lane, v[1]);
+      }
+    }
+    ++xe;
+    __syncthreads();
+  };
+
   for (int step = 0; step < p.n_steps; ++step) {
     const bool do_prof = (p.prof != nullptr) && cid == 0 && rank == 0 && step == p.prof_step;
     AMUSE_PROF(0);
@@ -443,13 +434,9 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       const int sl = r / T, tok = r - sl * T;
       float4 v;
       if (tok == 0) {
-        const float4 z = *reinterpret_cast<const float4*>(zs + sl * 128 + c4);
-        const float4 e = *reinterpret_cast<const float4*>(pe01 + c4);
-        v = make_float4(z.x + e.x, z.y + e.y, z.z + e.z, z.w + e.w);
+        v = add4(*reinterpret_cast<const float4*>(zs + sl * 128 + c4), *reinterpret_cast<const float4*>(pe01 + c4));
       } else if (tok == 1) {
-        const float4 z = *reinterpret_cast<const float4*>(tembs + c4);
-        const float4 e = *reinterpret_cast<const float4*>(pe01 + 128 + c4);
-        v = make_float4(z.x + e.x, z.y + e.y, z.z + e.z, z.w + e.w);
+        v = add4(*reinterpret_cast<const float4*>(tembs + c4), *reinterpret_cast<const float4*>(pe01 + 128 + c4));
       } else {
         v = *reinterpret_cast<const float4*>(Cs + (sl * 3 + tok - 2) * 128 + c4);
       }
@@ -459,26 +446,22 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     AMUSE_PROF(1);
 
     for (int layer = 0; layer < kLayers; ++layer) {
+      // Straight-line stages (a "stage machine" with one shared copy of the GEMM / epilogue code was
+      // tried to keep the loop inside the 32 KB instruction cache: it was 7% slower overall).
       // =============== output blocks: x = Linear(256->128)(cat(x, xs.pop())), K-split 64 per CTA
       if (layer >= 5) {
         const float* wt = wp_acquire(s, wp);
-        exchange_arm<RB>(s, xe, tid);
-        copy_params(par_bsk, wt + 64 * 128, 128, tid);
+        exchange_arm<RT>(s, xe, tid);
+        copy_params(par_tail, wt + 64 * 128, 128, tid);
         // my K slice of cat(x, skip): ranks 0,1 -> x[:, 64*rank ..], ranks 2,3 -> skip[:, 64*(rank-2) ..]
         const float* src = (rank < 2) ? (Xs + rank * 64) : (SK + (8 - layer) * kRMax * 128 + (rank - 2) * 64);
         float acc[5][4];
-        gemm5<128, 64, 4, KS, true>(src, 128, wt, role.rb, role.ks, lane, acc);
-        park<128, 4, true, RB>(RED, role, lane, acc);
+        gemm5<128, 4, (64 / KS) / 4>(src + (rb * 5) * 128 + ks * (64 / KS), 128,
+                                     wt + (ks * (32 / KS)) * 256 + lane * 2, acc);
+        park4<RT>(RED, rb, ks, lane, acc);
         __syncthreads();
         wp_release(s, wp, tid);
-        if (role.fold) {
-          fold<128, 4, true, RB>(RED, role, lane, acc);
-          broadcast_partial(s, xe, rank, role.rb, lane, acc);
-          exchange_wait(s, xe);
-          sum_norm_store<false, false>(s.Ps(xe & 1), par_bsk, nullptr, nullptr, Xs, nullptr, role.rb, lane, acc);
-        }
-        ++xe;
-        __syncthreads();
+        exchange_epilogue(par_tail, nullptr, nullptr, nullptr, -1, do_prof);
       }
       AMUSE_PROF(2 + layer * 10 + 0);
 
@@ -487,19 +470,35 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         const float* wt = wp_acquire(s, wp);
         copy_params(par_bqkv, wt + 128 * 96, 96, tid);
         float acc[5][3];
-        gemm5<96, 128, 3, KS, false>(Xs, 128, wt, role.rb, role.ks, lane, acc);
-        park<96, 3, false, RB>(RED, role, lane, acc);
-        __syncthreads();
-        wp_release(s, wp, tid);
-        if (role.fold) {
-          fold<96, 3, false, RB>(RED, role, lane, acc);
+        gemm5<96, 3, (128 / KS) / 4>(Xs + (rb * 5) * 128 + ks * (128 / KS), 128,
+                                     wt + (ks * (64 / KS)) * 192 + lane * 2, acc);
+        {
+          float* dst = RED + ((ks * RT + rb * 5) * 96) + lane;
 #pragma unroll
           for (int i = 0; i < 5; ++i) {
-            float* q = QKVs + (role.rb * 5 + i) * kQkvLd;
-            // nn.MultiheadAttention scales q (after bias) by head_dim^-0.5 before q.k^T
-            q[lane] = (acc[i][0] + par_bqkv[lane]) * 0.17677669529663687f;
-            q[32 + lane] = acc[i][1] + par_bqkv[32 + lane];
-            q[64 + lane] = acc[i][2] + par_bqkv[64 + lane];
+            dst[i * 96] = acc[i][0];
+            dst[i * 96 + 32] = acc[i][1];
+            dst[i * 96 + 64] = acc[i][2];
+          }
+        }
+        __syncthreads();
+        wp_release(s, wp, tid);
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          const int row = o ? row1 : row0;
+          if (o ? own1 : own0) {
+            float q = par_bqkv[lane], k = par_bqkv[32 + lane], v = par_bqkv[64 + lane];
+#pragma unroll
+            for (int c = 0; c < KS; ++c) {
+              const float* src = RED + ((c * RT + row) * 96) + lane;
+              q += src[0];
+              k += src[32];
+              v += src[64];
+            }
+            float* dst = QKVs + row * kQkvLd + lane;
+            dst[0] = q * 0.17677669529663687f;   // nn.MultiheadAttention scales q (after bias) by head_dim^-0.5
+            dst[32] = k;
+            dst[64] = v;
           }
         }
         __syncthreads();
@@ -552,72 +551,59 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       __syncthreads();
       AMUSE_PROF(2 + layer * 10 + 2);
 
-      // =============== out_proj, K-split by head -> DSMEM broadcast of the partial -> sum + LN1
+      // =============== out_proj, K-split by head -> st.async partial exchange -> sum + LN1
       {
         const float* wt = wp_acquire(s, wp);
-        exchange_arm<RB>(s, xe, tid);
-        copy_params(par_bo, wt + 32 * 128, 128, tid);
-        copy_params(par_ln1, wt + 32 * 128 + 128, 256, tid);
+        exchange_arm<RT>(s, xe, tid);
+        copy_params(par_tail, wt + 32 * 128, kTileTail, tid);
         float acc[5][4];
-        gemm5<128, 32, 4, KS, true>(Oh, kOhLd, wt, role.rb, role.ks, lane, acc);
-        park<128, 4, true, RB>(RED, role, lane, acc);
+        gemm5<128, 4, (32 / KS) / 4>(Oh + (rb * 5) * kOhLd + ks * (32 / KS), kOhLd,
+                                     wt + (ks * (16 / KS)) * 256 + lane * 2, acc);
+        park4<RT>(RED, rb, ks, lane, acc);
         __syncthreads();
         wp_release(s, wp, tid);
-        if (role.fold) {
-          fold<128, 4, true, RB>(RED, role, lane, acc);
-          broadcast_partial(s, xe, rank, role.rb, lane, acc);
-          exchange_wait(s, xe);
-          AMUSE_PROF(2 + layer * 10 + 3);
-          sum_norm_store<true, true>(s.Ps(xe & 1), par_bo, Xs, par_ln1, Xs, nullptr, role.rb, lane, acc);
-        }
-        ++xe;
-        __syncthreads();
+        exchange_epilogue(par_tail, Xs, par_tail + 128, nullptr, 2 + layer * 10 + 3, do_prof);
       }
       AMUSE_PROF(2 + layer * 10 + 4);
 
       // =============== FFN1: my 128 hidden units, erf-GELU
       {
         const float* wt = wp_acquire(s, wp);
-        copy_params(par_b1, wt + 128 * 128, 128, tid);
+        copy_params(par_tail, wt + 128 * 128, 128, tid);
         float acc[5][4];
-        gemm5<128, 128, 4, KS, true>(Xs, 128, wt, role.rb, role.ks, lane, acc);
-        park<128, 4, true, RB>(RED, role, lane, acc);
+        gemm5<128, 4, (128 / KS) / 4>(Xs + (rb * 5) * 128 + ks * (128 / KS), 128,
+                                      wt + (ks * (64 / KS)) * 256 + lane * 2, acc);
+        park4<RT>(RED, rb, ks, lane, acc);
         __syncthreads();
         wp_release(s, wp, tid);
-        if (role.fold) {
-          fold<128, 4, true, RB>(RED, role, lane, acc);
-          const float4 b = *reinterpret_cast<const float4*>(par_b1 + lane * 4);
+        const Row4 b = ld_row4(par_tail, lane);
 #pragma unroll
-          for (int i = 0; i < 5; ++i)
-            *reinterpret_cast<float4*>(Hs + (role.rb * 5 + i) * 128 + lane * 4) =
-                make_float4(gelu_erf(acc[i][0] + b.x), gelu_erf(acc[i][1] + b.y), gelu_erf(acc[i][2] + b.z),
-                            gelu_erf(acc[i][3] + b.w));
+        for (int o = 0; o < 2; ++o) {
+          const int row = o ? row1 : row0;
+          if (o ? own1 : own0) {
+            Row4 v = add4(gather4<RT, KS>(RED, row, lane), b);
+            v.lo = make_float2(gelu_erf(v.lo.x), gelu_erf(v.lo.y));
+            v.hi = make_float2(gelu_erf(v.hi.x), gelu_erf(v.hi.y));
+            st_row4(Hs + row * 128, lane, v);
+          }
         }
         __syncthreads();
       }
       AMUSE_PROF(2 + layer * 10 + 5);
 
-      // =============== FFN2, K-split over my 128 hidden units -> broadcast -> sum + LN2
+      // =============== FFN2, K-split over my 128 hidden units -> exchange -> sum + LN2
       {
         const float* wt = wp_acquire(s, wp);
-        exchange_arm<RB>(s, xe, tid);
-        copy_params(par_b2, wt + 128 * 128, 128, tid);
-        copy_params(par_ln2, wt + 128 * 128 + 128, 256, tid);
+        exchange_arm<RT>(s, xe, tid);
+        copy_params(par_tail, wt + 128 * 128, kTileTail, tid);
         float acc[5][4];
-        gemm5<128, 128, 4, KS, true>(Hs, 128, wt, role.rb, role.ks, lane, acc);
-        park<128, 4, true, RB>(RED, role, lane, acc);
+        gemm5<128, 4, (128 / KS) / 4>(Hs + (rb * 5) * 128 + ks * (128 / KS), 128,
+                                      wt + (ks * (64 / KS)) * 256 + lane * 2, acc);
+        park4<RT>(RED, rb, ks, lane, acc);
         __syncthreads();
         wp_release(s, wp, tid);
-        if (role.fold) {
-          fold<128, 4, true, RB>(RED, role, lane, acc);
-          broadcast_partial(s, xe, rank, role.rb, lane, acc);
-          exchange_wait(s, xe);
-          AMUSE_PROF(2 + layer * 10 + 6);
-          sum_norm_store<true, true>(s.Ps(xe & 1), par_b2, Xs, par_ln2, Xs,
-                                     (layer < 4) ? (SK + layer * kRMax * 128) : nullptr, role.rb, lane, acc);
-        }
-        ++xe;
-        __syncthreads();
+        exchange_epilogue(par_tail, Xs, par_tail + 128, (layer < 4) ? (SK + layer * kRMax * 128) : nullptr,
+                          2 + layer * 10 + 6, do_prof);
       }
       AMUSE_PROF(2 + layer * 10 + 7);
     }   // layers

@@ -18,11 +18,14 @@ constexpr int kMaxClusters = 33;       // co-resident 4-CTA clusters with ~225 K
 // Per-CTA-rank weight stream ("blob"): the tiles one CTA consumes during one denoiser
 // evaluation, in consumption order, each tile K-major ([k][n_local]) followed by the
 // bias / LayerNorm vectors its epilogue needs.  Sizes in floats.
+// Every 128-wide tile ends with the same 384-float tail: bias[128] | LayerNorm weight[128] | bias[128]
+// (zeros where a stage has no LayerNorm), so one generic stage routine serves all of them.
+constexpr int kTileTail = 384;
 constexpr int kTileQKV = 128 * 96 + 96;          // in_proj rows of head `rank`: q|k|v 32 each   + bias
-constexpr int kTileWO = 32 * 128 + 128 + 256;    // out_proj columns of head `rank` (K-split)    + bias + norm1
-constexpr int kTileW1 = 128 * 128 + 128;         // linear1 rows [128*rank, +128)                + bias
-constexpr int kTileW2 = 128 * 128 + 128 + 256;   // linear2 columns [128*rank, +128) (K-split)   + bias + norm2
-constexpr int kTileSK = 64 * 128 + 128;          // linear_blocks columns [64*rank, +64) (K-split) + bias
+constexpr int kTileWO = 32 * 128 + kTileTail;    // out_proj columns of head `rank` (K-split)    + bias + norm1
+constexpr int kTileW1 = 128 * 128 + kTileTail;   // linear1 rows [128*rank, +128)                + bias
+constexpr int kTileW2 = 128 * 128 + kTileTail;   // linear2 columns [128*rank, +128) (K-split)   + bias + norm2
+constexpr int kTileSK = 64 * 128 + kTileTail;    // linear_blocks columns [64*rank, +64) (K-split) + bias
 constexpr int kLayerFloats = kTileQKV + kTileWO + kTileW1 + kTileW2;
 constexpr int kBlobRankFloats = 9 * kLayerFloats + 4 * kTileSK;
 constexpr int kTileMax = kTileW2;

@@ -49,8 +49,8 @@ def main():
     # in-kernel cycle stamps of step 3
     eng.profile_arm(3)
     eng.denoise(l0, con, emo, sty, n_steps=8)
-    st = eng.profile_read(96)
-    names = ["skip", "qkv", "attn", "oproj+sync", "sum+ln1", "ffn1", "ffn2+sync", "sum+ln2"]
+    st = eng.profile_read(128)
+    names = ["skip", "qkv", "attn", "oproj+wait", "sum+ln1", "ffn1", "ffn2+wait", "sum+ln2"]
     print("step cycles total:", st[92] - st[0], " build-x:", st[1] - st[0])
     for l in range(9):
         base = 2 + l * 10
@@ -60,6 +60,7 @@ def main():
             row.append(st[base + j] - (prev if j == 0 else st[base + j - 1]))
         print(f"layer {l}: " + " ".join(f"{n}={c}" for n, c in zip(names, row)))
     print("final+update:", st[92] - st[2 + 8 * 10 + 7])
+    print("layer0 exchange waits: out_proj", st[5] - st[105], " ffn2", st[8] - st[108])
 
 
 if __name__ == "__main__":
