@@ -19,6 +19,7 @@
 #include "decode_kernels.cuh"
 #include "denoise_loop.cuh"
 #include "small_kernels.cuh"
+#include "tc_gemm.cuh"
 
 using namespace amuse;
 
@@ -899,6 +900,45 @@ int amuse_ast_features(amuse_ctx* ctx, int B, const float* fbank, float* con, fl
   int rc = ast::forward(ctx->astw, B, fbank, con, emo, sty, static_cast<cudaStream_t>(stream), &launches);
   ctx->launches += launches;
   if (rc) return fail(ctx, rc, "ast forward: %s", ast::last_error(ctx->astw));
+  return AMUSE_OK;
+}
+
+int amuse_debug_tc_gemm(amuse_ctx* ctx, int epi, int M, int N, int K, const float* A, const float* A2, int k_split,
+                        const float* W, const float* bias, const float* R, const float* ln, const float* cvec,
+                        int rows_per_clip, float* C, void* stream) {
+  if (!ctx || !A || !W || !bias || !C) return fail(ctx, AMUSE_E_INVALID, "bad argument");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int K1 = A2 ? k_split : K, K2 = K - K1;
+  const size_t nA = static_cast<size_t>(M) * K1, nA2 = static_cast<size_t>(M) * K2, nW = static_cast<size_t>(N) * K;
+  const size_t nC = static_cast<size_t>(M) * N, nR = R ? static_cast<size_t>(M) * 128 : 0;
+  DevBuf buf;
+  CU(buf.ensure(2 * (nA + nA2 + nW + nC + nR)));
+  float* p = buf.p;
+  auto take = [&](size_t n) { float* r = p; p += n; return r; };
+  float *a_hi = take(nA), *a_lo = take(nA), *a2_hi = take(nA2), *a2_lo = take(nA2), *w_hi = take(nW), *w_lo = take(nW);
+  float *c_hi = take(nC), *c_lo = take(nC), *r_hi = take(nR), *r_lo = take(nR);
+  CU(tc::split_planes(A, a_hi, a_lo, nA, st));
+  if (A2) CU(tc::split_planes(A2, a2_hi, a2_lo, nA2, st));
+  CU(tc::split_planes(W, w_hi, w_lo, nW, st));
+  if (R) CU(tc::split_planes(R, r_hi, r_lo, nR, st));
+  tc::GemmDesc d{};
+  d.A_hi = a_hi; d.A_lo = a_lo; d.lda = K1;
+  if (A2) { d.A2_hi = a2_hi; d.A2_lo = a2_lo; d.lda2 = K2; d.k_split = K1; }
+  d.W_hi = w_hi; d.W_lo = w_lo; d.ldw = K;
+  d.M = M; d.N = N; d.K = K; d.bias = bias;
+  d.C = C; d.C_hi = c_hi; d.C_lo = c_lo; d.ldc = N;
+  d.R_hi = r_hi; d.R_lo = r_lo; d.ldr = 128;
+  if (ln) { d.ln_g = ln; d.ln_b = ln + 128; d.ln2_g = ln + 256; d.ln2_b = ln + 384; }
+  d.cvec = cvec; d.rows_per_clip = rows_per_clip > 0 ? rows_per_clip : 1;
+  d.q_cols = 128; d.q_scale = 0.17677669529663687f;
+  CU(tc::gemm(epi, d, st));
+  ctx->launches++;
+  if (epi != tc::EPI_PLAIN && epi != tc::EPI_QKV) {   // recombine the planes for the caller
+    CU(launch_add_planes(c_hi, c_lo, C, nC, st));
+  }
+  CU(cudaStreamSynchronize(st));
+  buf.release();
   return AMUSE_OK;
 }
 

@@ -128,6 +128,16 @@ cudaError_t launch_rot6d(const float* feats, int feat_ld, long long n_frames, fl
   return cudaGetLastError();
 }
 
+__global__ void __launch_bounds__(256) add_planes_kernel(const float* __restrict__ hi, const float* __restrict__ lo,
+                                                         float* __restrict__ out, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = hi[i] + lo[i];
+}
+cudaError_t launch_add_planes(const float* hi, const float* lo, float* out, size_t n, cudaStream_t st) {
+  add_planes_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(hi, lo, out, n);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_rot6d_flat(const float* d6, long long n, float* aa, cudaStream_t st) {
   rot6d_flat_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(d6, n, aa);
   return cudaGetLastError();

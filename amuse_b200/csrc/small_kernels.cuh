@@ -1,5 +1,6 @@
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 
 namespace amuse {
 
@@ -18,5 +19,6 @@ cudaError_t launch_rot6d(const float* feats, int feat_ld, long long n_frames, fl
                          cudaStream_t st);
 
 cudaError_t launch_rot6d_flat(const float* d6, long long n, float* aa, cudaStream_t st);
+cudaError_t launch_add_planes(const float* hi, const float* lo, float* out, size_t n, cudaStream_t st);
 
 }  // namespace amuse

@@ -1,0 +1,432 @@
+// tcgen05 / TMEM / TMA GEMM with 3xTF32 accuracy (see tc_gemm.cuh).
+//
+// One CTA computes one 128 x 128 output tile.  192 threads, warp-specialised:
+//   warp 0      TMA producer: per 32-wide K block four 2-D tensor-map loads (A_hi, A_lo, W_hi, W_lo;
+//               128 rows x 128 B boxes, SWIZZLE_128B) into a 3-stage shared-memory ring, completion
+//               on the stage's "full" mbarrier (complete_tx::bytes)
+//   warp 1      TMEM allocation (128 columns) + MMA issue: one elected lane issues, per 8-wide k step,
+//               tcgen05.mma.cta_group::1.kind::tf32  D += A_hi.W_hi, A_lo.W_hi, A_hi.W_lo
+//               (operands straight from shared memory through UMMA descriptors), then
+//               tcgen05.commit -> the stage's "empty" mbarrier; after the last K block
+//               tcgen05.commit -> "accumulator ready"
+//   warps 2..5  epilogue: each warp owns the 32 TMEM lanes (= output rows) it may address
+//               (warp_id % 4), tcgen05.ld 32 columns at a time; a thread holds a whole output row, so
+//               bias / GELU / residual / LayerNorm need no cross-thread reduction
+// Accuracy: hi = cvt.rna.tf32(x), lo = x - hi (exact); dropping lo.lo leaves ~2^-21 relative error
+// per product, accumulated in fp32 in TMEM.
+#include "tc_gemm.cuh"
+
+#include <cudaTypedefs.h>
+
+#include <cstring>
+
+#include "common.cuh"
+
+namespace amuse {
+namespace tc {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32;        // BK fp32 = 128 B = one swizzle row
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 4;           // 16 KB (A and W tiles have the same shape)
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // A_hi, A_lo, W_hi, W_lo
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 128;
+constexpr int kSmemBytes = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+// UMMA shared-memory descriptor: K-major operand, SWIZZLE_128B, 8-row groups 1024 B apart.
+// Bit layout = cute::UMMA::SmemDescriptor (start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
+// version=1 [46,48) | layout_type [61,64), SWIZZLE_128B = 2).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1024u >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=B=TF32 [7,10)/[10,13)=2,
+// both K-major, N>>3 at [17,23), M>>4 at [24,29).
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  uint32_t h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  lo = x - hi;
+}
+
+__device__ __forceinline__ void row_layernorm128(float (&v)[128], const float* __restrict__ g,
+                                                 const float* __restrict__ b, float eps) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 128; ++i) s += v[i];
+  const float mean = s * (1.0f / 128.0f);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 128; ++i) {
+    v[i] -= mean;
+    q = fmaf(v[i], v[i], q);
+  }
+  const float rstd = rsqrtf(q * (1.0f / 128.0f) + eps);
+#pragma unroll
+  for (int i = 0; i < 128; ++i) v[i] = v[i] * rstd * __ldg(g + i) + __ldg(b + i);
+}
+
+}  // namespace
+
+template <int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+    tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                   const __grid_constant__ CUtensorMap tmA2_hi, const __grid_constant__ CUtensorMap tmA2_lo,
+                   const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                   const GemmDesc d) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;                 // [STAGES]
+  uint64_t* empty = bars + STAGES;       // [STAGES]
+  uint64_t* acc_ready = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int nkb = d.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA_hi);
+    prefetch_tmap(&tmA_lo);
+    prefetch_tmap(&tmW_hi);
+    prefetch_tmap(&tmW_lo);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_ready, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
+        uint8_t* st = smem + s * STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+        const int k0 = kb * BK;
+        if (k0 < d.k_split) {
+          tma_load_2d(st, &tmA_hi, &full[s], k0, m0);
+          tma_load_2d(st + TILE_BYTES, &tmA_lo, &full[s], k0, m0);
+        } else {
+          tma_load_2d(st, &tmA2_hi, &full[s], k0 - d.k_split, m0);
+          tma_load_2d(st + TILE_BYTES, &tmA2_lo, &full[s], k0 - d.k_split, m0);
+        }
+        tma_load_2d(st + 2 * TILE_BYTES, &tmW_hi, &full[s], k0, n0);
+        tma_load_2d(st + 3 * TILE_BYTES, &tmW_lo, &full[s], k0, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(&full[s], (kb / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {   // UMMA_K = 8 for TF32: advance 32 B inside the 128-B swizzle row
+          const uint64_t a_hi = umma_desc(base + k * 32);
+          const uint64_t a_lo = umma_desc(base + TILE_BYTES + k * 32);
+          const uint64_t w_hi = umma_desc(base + 2 * TILE_BYTES + k * 32);
+          const uint64_t w_lo = umma_desc(base + 3 * TILE_BYTES + k * 32);
+          umma_tf32(tmem_base, a_hi, w_hi, (kb | k) ? 1u : 0u);
+          umma_tf32(tmem_base, a_lo, w_hi, 1u);
+          umma_tf32(tmem_base, a_hi, w_lo, 1u);
+        }
+        umma_commit(&empty[s]);            // frees the stage once the MMAs above have read it
+      }
+      umma_commit(acc_ready);              // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                // TMEM lanes [32q, 32q+32) are the ones this warp may access
+    const int m = m0 + q * 32 + lane;      // my output row
+    const bool row_ok = m < d.M;
+    mbar_wait(acc_ready, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+
+    if (EPI == EPI_RES_LN_PLANES || EPI == EPI_RES_LN_CROSS_LN_PLANES) {
+      float v[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float t[32];
+        tmem_ld32(trow + c * 32, t);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[c * 32 + i] = t[i];
+      }
+      const size_t mr = row_ok ? m : 0;
+      const float4* rh = reinterpret_cast<const float4*>(d.R_hi + mr * d.ldr);
+      const float4* rl = reinterpret_cast<const float4*>(d.R_lo + mr * d.ldr);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float4 a = __ldg(rh + i), b = __ldg(rl + i);
+        v[i * 4 + 0] += __ldg(d.bias + i * 4 + 0) + (a.x + b.x);
+        v[i * 4 + 1] += __ldg(d.bias + i * 4 + 1) + (a.y + b.y);
+        v[i * 4 + 2] += __ldg(d.bias + i * 4 + 2) + (a.z + b.z);
+        v[i * 4 + 3] += __ldg(d.bias + i * 4 + 3) + (a.w + b.w);
+      }
+      row_layernorm128(v, d.ln_g, d.ln_b, d.ln_eps);
+      if (EPI == EPI_RES_LN_CROSS_LN_PLANES) {
+        const float* cv = d.cvec + static_cast<size_t>(mr / d.rows_per_clip) * 128;
+#pragma unroll
+        for (int i = 0; i < 128; ++i) v[i] += __ldg(cv + i);
+        row_layernorm128(v, d.ln2_g, d.ln2_b, d.ln_eps);
+      }
+      if (row_ok) {
+        float4* oh = reinterpret_cast<float4*>(d.C_hi + static_cast<size_t>(m) * d.ldc);
+        float4* ol = reinterpret_cast<float4*>(d.C_lo + static_cast<size_t>(m) * d.ldc);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float4 h, l;
+          split_tf32(v[i * 4 + 0], h.x, l.x);
+          split_tf32(v[i * 4 + 1], h.y, l.y);
+          split_tf32(v[i * 4 + 2], h.z, l.z);
+          split_tf32(v[i * 4 + 3], h.w, l.w);
+          oh[i] = h;
+          ol[i] = l;
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int nc = n0 + c * 32;
+        if (nc >= d.N) break;                    // warp-uniform
+        float v[32];
+        tmem_ld32(trow + c * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += (nc + i < d.N) ? __ldg(d.bias + nc + i) : 0.f;
+        if (EPI == EPI_QKV) {
+          if (nc < d.q_cols) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= d.q_scale;
+          }
+        }
+        if (EPI == EPI_GELU_PLANES) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+        }
+        if (EPI == EPI_RES_PLANES) {
+          const size_t mr = row_ok ? m : 0;
+          const float4* rh = reinterpret_cast<const float4*>(d.R_hi + mr * d.ldr + nc);
+          const float4* rl = reinterpret_cast<const float4*>(d.R_lo + mr * d.ldr + nc);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 a = __ldg(rh + i), b = __ldg(rl + i);
+            v[i * 4 + 0] += a.x + b.x;
+            v[i * 4 + 1] += a.y + b.y;
+            v[i * 4 + 2] += a.z + b.z;
+            v[i * 4 + 3] += a.w + b.w;
+          }
+        }
+        if (!row_ok) continue;
+        if (EPI == EPI_PLAIN || EPI == EPI_QKV) {
+          float* dst = d.C + static_cast<size_t>(m) * d.ldc + nc;
+          if (nc + 32 <= d.N && (d.ldc & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              reinterpret_cast<float4*>(dst)[i] = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (nc + i < d.N) dst[i] = v[i];
+          }
+        } else {
+          float4* oh = reinterpret_cast<float4*>(d.C_hi + static_cast<size_t>(m) * d.ldc + nc);
+          float4* ol = reinterpret_cast<float4*>(d.C_lo + static_cast<size_t>(m) * d.ldc + nc);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 h, l;
+            split_tf32(v[i * 4 + 0], h.x, l.x);
+            split_tf32(v[i * 4 + 1], h.y, l.y);
+            split_tf32(v[i * 4 + 2], h.z, l.z);
+            split_tf32(v[i * 4 + 3], h.w, l.w);
+            oh[i] = h;
+            ol[i] = l;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------- host side
+namespace {
+
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+cudaError_t load_encode() {
+  if (g_encode) return cudaSuccess;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess) return e;
+  if (qres != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  return cudaSuccess;
+}
+
+// row-major fp32 [rows][cols] with leading dimension ld (floats): box = 32 cols x 128 rows, 128-B swizzle
+cudaError_t make_map(CUtensorMap* tm, const float* ptr, int rows, int cols, int ld) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld & 3)) return cudaErrorInvalidValue;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 4};
+  const cuuint32_t box[2] = {BK, BM};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+template <int EPI>
+cudaError_t launch(const CUtensorMap* tm, const GemmDesc& d, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(tc_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((d.M + BM - 1) / BM, (d.N + BN - 1) / BN);
+  tc_gemm_kernel<EPI><<<grid, kThreads, kSmemBytes, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], d);
+  return cudaGetLastError();
+}
+
+__global__ void split_planes_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo,
+                                    size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float h, l;
+    split_tf32(src[i], h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+}  // namespace
+
+cudaError_t gemm(int epi, const GemmDesc& din, cudaStream_t st) {
+  GemmDesc d = din;
+  if (d.K % BK != 0 || d.M < 1 || d.N < 1) return cudaErrorInvalidValue;
+  if (!d.A2_hi) d.k_split = d.K;
+  if (d.k_split % BK != 0) return cudaErrorInvalidValue;
+  if ((epi == EPI_RES_LN_PLANES || epi == EPI_RES_LN_CROSS_LN_PLANES) && d.N != 128) return cudaErrorInvalidValue;
+  if (d.ln_eps == 0.f) d.ln_eps = kLnEps;
+  cudaError_t e = load_encode();
+  if (e != cudaSuccess) return e;
+  CUtensorMap tm[6];
+  if ((e = make_map(&tm[0], d.A_hi, d.M, d.k_split, d.lda)) != cudaSuccess) return e;
+  if ((e = make_map(&tm[1], d.A_lo, d.M, d.k_split, d.lda)) != cudaSuccess) return e;
+  if (d.A2_hi) {
+    if ((e = make_map(&tm[2], d.A2_hi, d.M, d.K - d.k_split, d.lda2)) != cudaSuccess) return e;
+    if ((e = make_map(&tm[3], d.A2_lo, d.M, d.K - d.k_split, d.lda2)) != cudaSuccess) return e;
+  } else {
+    tm[2] = tm[0];
+    tm[3] = tm[1];
+  }
+  if ((e = make_map(&tm[4], d.W_hi, d.N, d.K, d.ldw)) != cudaSuccess) return e;
+  if ((e = make_map(&tm[5], d.W_lo, d.N, d.K, d.ldw)) != cudaSuccess) return e;
+  switch (epi) {
+    case EPI_PLAIN: return launch<EPI_PLAIN>(tm, d, st);
+    case EPI_QKV: return launch<EPI_QKV>(tm, d, st);
+    case EPI_PLANES: return launch<EPI_PLANES>(tm, d, st);
+    case EPI_GELU_PLANES: return launch<EPI_GELU_PLANES>(tm, d, st);
+    case EPI_RES_LN_PLANES: return launch<EPI_RES_LN_PLANES>(tm, d, st);
+    case EPI_RES_LN_CROSS_LN_PLANES: return launch<EPI_RES_LN_CROSS_LN_PLANES>(tm, d, st);
+    case EPI_RES_PLANES: return launch<EPI_RES_PLANES>(tm, d, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t split_planes(const float* src, float* hi, float* lo, size_t n, cudaStream_t st) {
+  split_planes_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(src, hi, lo, n);
+  return cudaGetLastError();
+}
+
+void split_host(const float* src, float* hi, float* lo, size_t n) {
+  for (size_t i = 0; i < n; ++i) {
+    uint32_t u;
+    std::memcpy(&u, &src[i], 4);
+    // round to nearest (ties away, like cvt.rna) on the 13 dropped mantissa bits
+    uint32_t h = (u + 0x1000u) & 0xFFFFE000u;
+    if ((u & 0x7F800000u) == 0x7F800000u) h = u;   // inf / nan untouched
+    float hf;
+    std::memcpy(&hf, &h, 4);
+    hi[i] = hf;
+    lo[i] = src[i] - hf;
+  }
+}
+
+}  // namespace tc
+}  // namespace amuse

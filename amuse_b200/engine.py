@@ -195,6 +195,20 @@ class Engine:
                                                     self._stream()))
         return con, emo, sty
 
+    def debug_tc_gemm(self, epi: int, A, W, bias, A2=None, R=None, ln=None, cvec=None, rows_per_clip=1):
+        """Unit-test hook for the tcgen05 3xTF32 GEMM: epi(A [| A2] . W^T + bias) -> [M, N] fp32."""
+        A, W, bias = self._dev(A), self._dev(W), self._dev(bias)
+        A2, R, ln, cvec = self._dev(A2), self._dev(R), self._dev(ln), self._dev(cvec)
+        M, K1 = A.shape
+        K = K1 + (A2.shape[1] if A2 is not None else 0)
+        N = W.shape[0]
+        out = torch.empty(M, N, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.amuse_debug_tc_gemm(self._h, epi, M, N, K, _ptr(A), _ptr(A2), K1, _ptr(W), _ptr(bias),
+                                                     _ptr(R), _ptr(ln), _ptr(cvec), rows_per_clip, _ptr(out),
+                                                     self._stream()))
+        return out
+
     # ------------------------------------------------------------------ introspection
     def launch_count(self) -> int:
         return int(self.lib.amuse_launch_count(self._h))
