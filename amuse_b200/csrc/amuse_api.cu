@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -71,6 +72,8 @@ const char* kBlocks[9] = {"input_blocks.0", "input_blocks.1", "input_blocks.2", 
 // ---- decoder weights on the device (all K-major) ----------------------------------------
 struct DecLayerW {
   size_t wqkv_t, bqkv, wo_t, bo, ln1, w1_t, b1, w2_t, b2, ln2, ln3;   // offsets (floats) into dec arena
+  // tcgen05 path: the reference's own [N][K] layout, split into TF32 hi/lo planes (hi at off, lo at off + n)
+  size_t p_qkv, p_wo, p_w1, p_w2;
 };
 struct DecW {
   DevBuf arena;
@@ -78,6 +81,7 @@ struct DecW {
   size_t skip_t[4], bskip[4];
   size_t wv_t, bv, wco_t, bco;   // [9][128][128] / [9][128] cross-attention value + out projections
   size_t norm, final_t, bfinal, pe;
+  size_t p_skip[4], p_final, p_pe;   // planes (hi | lo)
   bool ready = false;
 };
 
@@ -102,6 +106,8 @@ struct amuse_ctx {
   // workspaces
   DevBuf cond, lat_tmp, lat_out, one_coef;
   DevBuf dXA, dXB, dXC, dQKV, dO, dH, dSkip, dFeats, dCvec, dZero;
+  DevBuf tX[3], tSkip, tO, tH;   // tcgen05 decoder path: activation planes (hi | lo halves)
+  bool dec_use_tc = true;        // decoder GEMMs on tcgen05 (3xTF32); false = fp32 FFMA kernels
   DevBuf h2d;   // staging for the *_host entry point
   long long* d_prof = nullptr;
   int prof_step = -1;
@@ -430,6 +436,15 @@ int pack_decoder(amuse_ctx* ctx, cudaStream_t st) {
     NEED(w2, b + ".linear2.weight", 128, 512);
     NEED(b2, b + ".linear2.bias", 128);
     DecLayerW& L = d.L[l];
+    auto put_planes = [&](const float* w, size_t n) {
+      const size_t o = put(2 * n);
+      tc::split_host(w, &ar[o], &ar[o + n], n);
+      return o;
+    };
+    L.p_qkv = put_planes(inw->data.data(), 384 * 128);
+    L.p_wo = put_planes(ow->data.data(), 128 * 128);
+    L.p_w1 = put_planes(w1->data.data(), 512 * 128);
+    L.p_w2 = put_planes(w2->data.data(), 128 * 512);
     L.wqkv_t = put(128 * 384);
     transpose_into(&ar[L.wqkv_t], inw->data.data(), 384, 128);
     L.bqkv = put(384);
@@ -464,6 +479,8 @@ int pack_decoder(amuse_ctx* ctx, cudaStream_t st) {
     const std::string s = P + "decoder.linear_blocks." + std::to_string(i);
     NEED(sw, s + ".weight", 128, 256);
     NEED(sb, s + ".bias", 128);
+    d.p_skip[i] = put(2 * 128 * 256);
+    tc::split_host(sw->data.data(), &ar[d.p_skip[i]], &ar[d.p_skip[i] + 128 * 256], 128 * 256);
     d.skip_t[i] = put(256 * 128);
     transpose_into(&ar[d.skip_t[i]], sw->data.data(), 128, 256);
     d.bskip[i] = put(128);
@@ -479,11 +496,15 @@ int pack_decoder(amuse_ctx* ctx, cudaStream_t st) {
   d.final_t = put(128 * 336);   // [128][336], columns 333..335 zero
   for (int k = 0; k < 128; ++k)
     for (int n = 0; n < kFeats; ++n) ar[d.final_t + static_cast<size_t>(k) * 336 + n] = fw->data[static_cast<size_t>(n) * 128 + k];
+  d.p_final = put(2 * kFeats * 128);
+  tc::split_host(fw->data.data(), &ar[d.p_final], &ar[d.p_final + kFeats * 128], static_cast<size_t>(kFeats) * 128);
   d.bfinal = put(336);
   std::memcpy(&ar[d.bfinal], fb->data.data(), kFeats * 4);
   NEED(pe, P + "query_pos_decoder.pe", 500, 1, 128);
   d.pe = put(500 * 128);
   std::memcpy(&ar[d.pe], pe->data.data(), 500 * 128 * 4);
+  d.p_pe = put(2 * 500 * 128);
+  tc::split_host(pe->data.data(), &ar[d.p_pe], &ar[d.p_pe + 500 * 128], 500 * 128);
   CU(d.arena.ensure(ar.size()));
   CU(cudaMemcpyAsync(d.arena.p, ar.data(), ar.size() * 4, cudaMemcpyHostToDevice, st));
   CU(cudaStreamSynchronize(st));
@@ -655,6 +676,130 @@ int run_decode(amuse_ctx* ctx, int B, const float* latents, float* feats6d, floa
   return AMUSE_OK;
 }
 
+// MotionPrior.decode on the tensor cores: every GEMM is a tcgen05 3xTF32 launch (tc_gemm.cu) with
+// the bias / q-scale / GELU / residual + LayerNorm (+ collapsed cross-attention + LayerNorm)
+// epilogues fused; activations travel between kernels as TF32 hi/lo planes (value = hi + lo).
+// Same buffer plan as run_decode: layer input cur = XB | SK[l-1] | XC, after attention XA, output SK[l] | XB.
+int run_decode_tc(amuse_ctx* ctx, int B, const float* latents, float* feats6d, float* poses, float* trans,
+                  cudaStream_t st) {
+  using namespace dec;
+  DecW& d = ctx->dec;
+  const float* W = d.arena.p;
+  const int chunk = ctx->dec_chunk;
+  const size_t Mc = static_cast<size_t>(std::min(B, chunk)) * kFrames;
+  const size_t n128 = Mc * 128;
+  for (int i = 0; i < 3; ++i) CU(ctx->tX[i].ensure(2 * n128));
+  CU(ctx->tSkip.ensure(2 * n128 * 4));
+  CU(ctx->tO.ensure(2 * n128));
+  CU(ctx->tH.ensure(2 * Mc * 512));
+  CU(ctx->dQKV.ensure(Mc * 384));
+  CU(ctx->dFeats.ensure(Mc * kFeats));
+  CU(ctx->dCvec.ensure(static_cast<size_t>(9) * B * 128));
+  if (!ctx->dZero.p) {
+    CU(ctx->dZero.ensure(128));
+    CU(cudaMemset(ctx->dZero.p, 0, 128 * sizeof(float)));
+  }
+  struct P {
+    float* hi;
+    float* lo;
+  };
+  auto planes = [&](DevBuf& b, size_t n, size_t idx = 0) { return P{b.p + idx * 2 * n, b.p + idx * 2 * n + n}; };
+  const P XA = planes(ctx->tX[0], n128), XB = planes(ctx->tX[1], n128), XC = planes(ctx->tX[2], n128);
+  const P O = planes(ctx->tO, n128), H = planes(ctx->tH, Mc * 512);
+  auto SK = [&](int i) { return planes(ctx->tSkip, n128, static_cast<size_t>(i)); };
+
+  CU(launch_cross_vectors(latents, W + d.wv_t, W + d.bv, W + d.wco_t, W + d.bco, ctx->dCvec.p, B, st));
+  ctx->launches++;
+
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nb = std::min(chunk, B - b0);
+    const int M = nb * kFrames;
+    // queries = zeros + pe[:300] (vae.py:221,253), as planes
+    CU(launch_broadcast_rows(W + d.p_pe, XB.hi, nb, kFrames, st));
+    CU(launch_broadcast_rows(W + d.p_pe + 500 * 128, XB.lo, nb, kFrames, st));
+    ctx->launches += 2;
+    P cur = XB;
+    for (int l = 0; l < 9; ++l) {
+      const DecLayerW& L = d.L[l];
+      tc::GemmDesc g{};
+      if (l >= 5) {   // x = Linear(cat(x, xs.pop()))
+        const P sk = SK(8 - l);
+        g.A_hi = cur.hi; g.A_lo = cur.lo; g.lda = 128;
+        g.A2_hi = sk.hi; g.A2_lo = sk.lo; g.lda2 = 128; g.k_split = 128;
+        g.W_hi = W + d.p_skip[l - 5]; g.W_lo = g.W_hi + 128 * 256; g.ldw = 256;
+        g.M = M; g.N = 128; g.K = 256; g.bias = W + d.bskip[l - 5];
+        g.C_hi = XC.hi; g.C_lo = XC.lo; g.ldc = 128;
+        CU(tc::gemm(tc::EPI_PLANES, g, st));
+        ctx->launches++;
+        cur = XC;
+      }
+      // packed in_proj -> q (pre-scaled) | k | v, plain fp32 for the attention kernel
+      g = tc::GemmDesc{};
+      g.A_hi = cur.hi; g.A_lo = cur.lo; g.lda = 128;
+      g.W_hi = W + L.p_qkv; g.W_lo = g.W_hi + 384 * 128; g.ldw = 128;
+      g.M = M; g.N = 384; g.K = 128; g.bias = W + L.bqkv;
+      g.C = ctx->dQKV.p; g.ldc = 384; g.q_cols = 128; g.q_scale = 0.17677669529663687f;
+      CU(tc::gemm(tc::EPI_QKV, g, st));
+      CU(launch_self_attention_planes(ctx->dQKV.p, O.hi, O.lo, nb, kFrames, st));
+      // y = norm2(norm1(x + out_proj(o)) + cross_vector)
+      g = tc::GemmDesc{};
+      g.A_hi = O.hi; g.A_lo = O.lo; g.lda = 128;
+      g.W_hi = W + L.p_wo; g.W_lo = g.W_hi + 128 * 128; g.ldw = 128;
+      g.M = M; g.N = 128; g.K = 128; g.bias = W + L.bo;
+      g.R_hi = cur.hi; g.R_lo = cur.lo; g.ldr = 128;
+      g.ln_g = W + L.ln1; g.ln_b = W + L.ln1 + 128; g.ln2_g = W + L.ln2; g.ln2_b = W + L.ln2 + 128;
+      g.cvec = ctx->dCvec.p + (static_cast<size_t>(l) * B + b0) * 128; g.rows_per_clip = kFrames;
+      g.C_hi = XA.hi; g.C_lo = XA.lo; g.ldc = 128;
+      CU(tc::gemm(tc::EPI_RES_LN_CROSS_LN_PLANES, g, st));
+      // h = gelu(linear1(y))
+      g = tc::GemmDesc{};
+      g.A_hi = XA.hi; g.A_lo = XA.lo; g.lda = 128;
+      g.W_hi = W + L.p_w1; g.W_lo = g.W_hi + 512 * 128; g.ldw = 128;
+      g.M = M; g.N = 512; g.K = 128; g.bias = W + L.b1;
+      g.C_hi = H.hi; g.C_lo = H.lo; g.ldc = 512;
+      CU(tc::gemm(tc::EPI_GELU_PLANES, g, st));
+      // out = norm3(y + linear2(h))  [+ decoder.norm after the last block]
+      const P out = (l < 4) ? SK(l) : XB;
+      g = tc::GemmDesc{};
+      g.A_hi = H.hi; g.A_lo = H.lo; g.lda = 512;
+      g.W_hi = W + L.p_w2; g.W_lo = g.W_hi + 128 * 512; g.ldw = 512;
+      g.M = M; g.N = 128; g.K = 512; g.bias = W + L.b2;
+      g.R_hi = XA.hi; g.R_lo = XA.lo; g.ldr = 128;
+      g.ln_g = W + L.ln3; g.ln_b = W + L.ln3 + 128;
+      g.C_hi = out.hi; g.C_lo = out.lo; g.ldc = 128;
+      if (l == 8) {
+        g.cvec = ctx->dZero.p; g.rows_per_clip = 1 << 30;
+        g.ln2_g = W + d.norm; g.ln2_b = W + d.norm + 128;
+        CU(tc::gemm(tc::EPI_RES_LN_CROSS_LN_PLANES, g, st));
+      } else {
+        CU(tc::gemm(tc::EPI_RES_LN_PLANES, g, st));
+      }
+      ctx->launches += 5;
+      cur = out;
+    }
+    float* feats = feats6d ? feats6d + static_cast<size_t>(b0) * kFrames * kFeats : ctx->dFeats.p;
+    tc::GemmDesc g{};
+    g.A_hi = cur.hi; g.A_lo = cur.lo; g.lda = 128;
+    g.W_hi = W + d.p_final; g.W_lo = g.W_hi + kFeats * 128; g.ldw = 128;
+    g.M = M; g.N = kFeats; g.K = 128; g.bias = W + d.bfinal;
+    g.C = feats; g.ldc = kFeats;
+    CU(tc::gemm(tc::EPI_PLAIN, g, st));
+    ctx->launches++;
+    if (poses) {
+      CU(launch_rot6d(feats, kFeats, static_cast<long long>(M), poses + static_cast<size_t>(b0) * kFrames * 165,
+                      trans ? trans + static_cast<size_t>(b0) * kFrames * 3 : nullptr, st));
+      ctx->launches++;
+    }
+  }
+  return AMUSE_OK;
+}
+
+int run_decode_any(amuse_ctx* ctx, int B, const float* latents, float* feats6d, float* poses, float* trans,
+                   cudaStream_t st) {
+  return ctx->dec_use_tc ? run_decode_tc(ctx, B, latents, feats6d, poses, trans, st)
+                         : run_decode(ctx, B, latents, feats6d, poses, trans, st);
+}
+
 int check_ready(amuse_ctx* ctx, bool den, bool dec) {
   if (!ctx) return AMUSE_E_INVALID;
   if (den && !ctx->den.ready) return fail(ctx, AMUSE_E_STATE, "denoiser weights not finalized");
@@ -681,6 +826,7 @@ int amuse_create(amuse_ctx** out, int device_ordinal) {
   amuse_ctx* c = new amuse_ctx();
   c->device = device_ordinal;
   default_alphas(c->alphas_cumprod);
+  if (const char* e = getenv("AMUSE_DECODE_FFMA")) c->dec_use_tc = !(e[0] == '1');   // A/B switch for measurements
   if (cudaMalloc(&c->d_prof, 128 * sizeof(long long)) != cudaSuccess) {
     delete c;
     return AMUSE_E_CUDA;
@@ -696,7 +842,8 @@ void amuse_destroy(amuse_ctx* ctx) {
   drop_schedules(ctx);
   DevBuf* bufs[] = {&ctx->den.blob, &ctx->den.misc, &ctx->dec.arena, &ctx->cond, &ctx->lat_tmp, &ctx->lat_out,
                     &ctx->one_coef, &ctx->dXA, &ctx->dXB, &ctx->dXC, &ctx->dQKV, &ctx->dO, &ctx->dH, &ctx->dSkip,
-                    &ctx->dFeats, &ctx->dCvec, &ctx->dZero, &ctx->h2d};
+                    &ctx->dFeats, &ctx->dCvec, &ctx->dZero, &ctx->h2d, &ctx->tX[0], &ctx->tX[1], &ctx->tX[2],
+                    &ctx->tSkip, &ctx->tO, &ctx->tH};
   for (DevBuf* b : bufs) b->release();
   ast::release(ctx->astw);
   if (ctx->d_prof) cudaFree(ctx->d_prof);
@@ -827,7 +974,7 @@ int amuse_decode(amuse_ctx* ctx, int B, const float* latents, float* feats6d, fl
   if (int rc = check_ready(ctx, false, true)) return rc;
   if (B < 1 || !latents || (!feats6d && !poses)) return fail(ctx, AMUSE_E_INVALID, "bad argument");
   cudaSetDevice(ctx->device);
-  return run_decode(ctx, B, latents, feats6d, poses, trans, static_cast<cudaStream_t>(stream));
+  return run_decode_any(ctx, B, latents, feats6d, poses, trans, static_cast<cudaStream_t>(stream));
 }
 
 int amuse_rot6d_to_axis_angle(amuse_ctx* ctx, int64_t n, const float* d6, float* axis_angle, void* stream) {
@@ -854,7 +1001,7 @@ int amuse_diffusion_backward(amuse_ctx* ctx, int B, int n_steps, int sampler, fl
   if (int rc = amuse_denoise(ctx, B, n_steps, sampler, eta, clip_sample, latents0, z_con, z_emo, z_sty, step_noise,
                              seed, z, stream))
     return rc;
-  return run_decode(ctx, B, z, feats6d, poses, trans, static_cast<cudaStream_t>(stream));
+  return run_decode_any(ctx, B, z, feats6d, poses, trans, static_cast<cudaStream_t>(stream));
 }
 
 int amuse_diffusion_backward_host(amuse_ctx* ctx, int B, int n_steps, int sampler, float eta, int clip_sample,

@@ -30,6 +30,13 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+__device__ __forceinline__ void split_tf32_rna(float x, float& hi, float& lo) {
+  uint32_t h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  lo = x - hi;
+}
+
 __device__ __forceinline__ float group16_sum(float v) {
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -199,8 +206,9 @@ cudaError_t launch_gemm(int epi, const GemmArgs& a, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------- self attention
+template <bool PLANES>
 __global__ void __launch_bounds__(128) self_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out,
-                                                             int frames) {
+                                                             float* __restrict__ out_lo, int frames) {
   extern __shared__ __align__(16) float kv[];
   float* Ks = kv;
   float* Vs = kv + frames * 32;
@@ -270,26 +278,45 @@ __global__ void __launch_bounds__(128) self_attention_kernel(const float* __rest
   }
   if (valid) {
     const float inv = 1.0f / l;
-    float* dst = out + (static_cast<size_t>(b) * frames + qi) * 128 + h * 32;
+    const size_t off = (static_cast<size_t>(b) * frames + qi) * 128 + h * 32;
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      *reinterpret_cast<float4*>(dst + c * 4) =
-          make_float4(acc[c * 4 + 0] * inv, acc[c * 4 + 1] * inv, acc[c * 4 + 2] * inv, acc[c * 4 + 3] * inv);
+    for (int c = 0; c < 8; ++c) {
+      const float4 v = make_float4(acc[c * 4 + 0] * inv, acc[c * 4 + 1] * inv, acc[c * 4 + 2] * inv, acc[c * 4 + 3] * inv);
+      if (PLANES) {   // TF32 hi/lo planes for the tcgen05 out_proj GEMM
+        float4 hi, lo;
+        split_tf32_rna(v.x, hi.x, lo.x);
+        split_tf32_rna(v.y, hi.y, lo.y);
+        split_tf32_rna(v.z, hi.z, lo.z);
+        split_tf32_rna(v.w, hi.w, lo.w);
+        *reinterpret_cast<float4*>(out + off + c * 4) = hi;
+        *reinterpret_cast<float4*>(out_lo + off + c * 4) = lo;
+      } else {
+        *reinterpret_cast<float4*>(out + off + c * 4) = v;
+      }
+    }
   }
 }
 
-cudaError_t launch_self_attention(const float* qkv, float* out, int clips, int frames, cudaStream_t st) {
+template <bool PLANES>
+static cudaError_t launch_attn(const float* qkv, float* out, float* out_lo, int clips, int frames, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(frames) * 64 * sizeof(float);
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(self_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(self_attention_kernel<PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     configured = smem;
   }
   dim3 grid((frames + 127) / 128, kHeads, clips);
-  self_attention_kernel<<<grid, 128, smem, st>>>(qkv, out, frames);
+  self_attention_kernel<PLANES><<<grid, 128, smem, st>>>(qkv, out, out_lo, frames);
   return cudaGetLastError();
+}
+cudaError_t launch_self_attention(const float* qkv, float* out, int clips, int frames, cudaStream_t st) {
+  return launch_attn<false>(qkv, out, nullptr, clips, frames, st);
+}
+cudaError_t launch_self_attention_planes(const float* qkv, float* out_hi, float* out_lo, int clips, int frames,
+                                         cudaStream_t st) {
+  return launch_attn<true>(qkv, out_hi, out_lo, clips, frames, st);
 }
 
 // ------------------------------------------------------------------------- 1-key cross attention

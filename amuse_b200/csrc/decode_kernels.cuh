@@ -34,6 +34,9 @@ cudaError_t launch_gemm(int epi, const GemmArgs& a, cudaStream_t st);
 cudaError_t launch_self_attention(const float* qkv /*[M][384]*/, float* out /*[M][128]*/, int clips, int frames,
                                   cudaStream_t st);
 
+cudaError_t launch_self_attention_planes(const float* qkv, float* out_hi, float* out_lo, int clips, int frames,
+                                         cudaStream_t st);
+
 // cvec[l][b] = out_proj_l(W_v,l z_b + b_v,l) + b_o,l for the 9 decoder layers (1-key cross attention).
 cudaError_t launch_cross_vectors(const float* z /*[B][128]*/, const float* wv_t /*[9][128][128]*/,
                                  const float* bv /*[9][128]*/, const float* wo_t /*[9][128][128]*/,
