@@ -890,11 +890,11 @@ int amuse_finalize_weights(amuse_ctx* ctx, void* stream) {
   cudaSetDevice(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   bool any = false;
-  if (any_with_prefix(ctx, "denoiser.")) {
+  if (find(ctx, "denoiser.encoder.norm.weight")) {   // (a bare "denoiser.time_proj.freqs" table does not count)
     if (int rc = pack_denoiser(ctx, st)) return rc;
     any = true;
   }
-  if (any_with_prefix(ctx, "vae.")) {
+  if (find(ctx, "vae.decoder.norm.weight")) {
     if (int rc = pack_decoder(ctx, st)) return rc;
     any = true;
   }

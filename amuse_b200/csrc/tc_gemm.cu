@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           const float4* rl = reinterpret_cast<const float4*>(d.R_lo + mr * d.ldr + nc);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 a = __ldg(rh + i), b = __ldg(rl + i);
+            const float4 a = rh[i], b = rl[i];   // plain loads: C may alias R (in-place residual update)
             v[i * 4 + 0] += a.x + b.x;
             v[i * 4 + 1] += a.y + b.y;
             v[i * 4 + 2] += a.z + b.z;
