@@ -133,7 +133,11 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  // blockIdx.x walks the N tiles of one M block: the CTAs that share an A tile are launched together, so
+  // the (large, streamed) A planes are read from HBM once and hit L2 for the other N tiles, while the
+  // (small) W planes stay L2-resident.  (With M fastest the A planes were re-read once per N tile:
+  // 3.0 GB of DRAM reads for fc2 -- ncu, profiles/r01_tc_gemm_ast_full.txt.)
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int nkb = d.K / BK;
 
   if (warp == 0 && lane == 0) {
@@ -358,7 +362,7 @@ cudaError_t launch(const CUtensorMap* tm, const GemmDesc& d, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  dim3 grid((d.M + BM - 1) / BM, (d.N + BN - 1) / BN);
+  dim3 grid((d.N + BN - 1) / BN, (d.M + BM - 1) / BM);
   tc_gemm_kernel<EPI><<<grid, kThreads, kSmemBytes, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], d);
   return cudaGetLastError();
 }

@@ -16,6 +16,7 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "sm__cycles_active.avg"]
 
@@ -72,5 +73,6 @@ OUT.mkdir(exist_ok=True)
 launches()
 full("prof_denoise.ncu-rep", "denoise_loop_full")
 full("prof_decode_gemm.ncu-rep", "decode_gemm_full", n_show=3)
+full("prof_tc_gemm_ast.ncu-rep", "tc_gemm_ast_full", n_show=4)
 for p in sorted(OUT.glob(f"{TAG}_*")):
     print(p.name, p.stat().st_size)
