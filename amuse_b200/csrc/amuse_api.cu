@@ -563,6 +563,10 @@ int run_denoise(amuse_ctx* ctx, int B, Schedule& sc, int clip, const float* late
   p.clip = clip;
   p.seed = seed;
   p.seed_elem_base = elem_base;
+  {
+    static const int skew = getenv("AMUSE_GROUP_SKEW") ? atoi(getenv("AMUSE_GROUP_SKEW")) : 1500;
+    p.group_skew_cycles = skew;
+  }
   CU(dn::launch(p, st));
   ctx->launches++;
   ctx->prof_step = -1;
