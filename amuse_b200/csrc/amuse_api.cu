@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "decode_kernels.cuh"
 #include "denoise_loop.cuh"
+#include "fbank_kernel.cuh"
 #include "small_kernels.cuh"
 #include "tc_gemm.cuh"
 
@@ -109,6 +110,7 @@ struct amuse_ctx {
   DevBuf tX[3], tSkip, tO, tH;   // tcgen05 decoder path: activation planes (hi | lo halves)
   bool dec_use_tc = true;        // decoder GEMMs on tcgen05 (3xTF32); false = fp32 FFMA kernels
   DevBuf h2d;   // staging for the *_host entry point
+  DevBuf mel_t; // [257][128] mel filterbank weights (K-major)
   long long* d_prof = nullptr;
   int prof_step = -1;
   int64_t launches = 0;
@@ -563,10 +565,6 @@ int run_denoise(amuse_ctx* ctx, int B, Schedule& sc, int clip, const float* late
   p.clip = clip;
   p.seed = seed;
   p.seed_elem_base = elem_base;
-  {
-    static const int skew = getenv("AMUSE_GROUP_SKEW") ? atoi(getenv("AMUSE_GROUP_SKEW")) : 1500;
-    p.group_skew_cycles = skew;
-  }
   CU(dn::launch(p, st));
   ctx->launches++;
   ctx->prof_step = -1;
@@ -847,7 +845,7 @@ void amuse_destroy(amuse_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->den.blob, &ctx->den.misc, &ctx->dec.arena, &ctx->cond, &ctx->lat_tmp, &ctx->lat_out,
                     &ctx->one_coef, &ctx->dXA, &ctx->dXB, &ctx->dXC, &ctx->dQKV, &ctx->dO, &ctx->dH, &ctx->dSkip,
                     &ctx->dFeats, &ctx->dCvec, &ctx->dZero, &ctx->h2d, &ctx->tX[0], &ctx->tX[1], &ctx->tX[2],
-                    &ctx->tSkip, &ctx->tO, &ctx->tH};
+                    &ctx->tSkip, &ctx->tO, &ctx->tH, &ctx->mel_t};
   for (DevBuf* b : bufs) b->release();
   ast::release(ctx->astw);
   if (ctx->d_prof) cudaFree(ctx->d_prof);
@@ -1090,6 +1088,24 @@ int amuse_debug_tc_gemm(amuse_ctx* ctx, int epi, int M, int N, int K, const floa
   }
   CU(cudaStreamSynchronize(st));
   buf.release();
+  return AMUSE_OK;
+}
+
+int amuse_fbank(amuse_ctx* ctx, int B, int n_samples, const float* wave, float norm_mean, float norm_std,
+                float* fbank, void* stream) {
+  if (!ctx || B < 1 || !wave || !fbank) return fail(ctx, AMUSE_E_INVALID, "bad argument");
+  if (n_samples < 400) return fail(ctx, AMUSE_E_INVALID, "need at least one 25 ms frame (400 samples)");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!ctx->mel_t.p) {
+    std::vector<float> m(257 * 128);
+    fb::mel_banks_host(m.data());
+    CU(ctx->mel_t.ensure(m.size()));
+    CU(cudaMemcpy(ctx->mel_t.p, m.data(), m.size() * 4, cudaMemcpyHostToDevice));
+    CU(fb::upload_tables());
+  }
+  CU(fb::launch(wave, B, n_samples, ctx->mel_t.p, norm_mean, norm_std, fbank, st));
+  ctx->launches++;
   return AMUSE_OK;
 }
 

@@ -32,8 +32,6 @@
 
 #include <curand_kernel.h>
 
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace amuse {
@@ -284,9 +282,7 @@ __device__ __forceinline__ void layernorm2(Row4 (&v)[2], const float* lnp, int l
 __device__ __forceinline__ void copy_params(float* dst, const float* src, int n, int tid) {
   for (int i = tid; i < n; i += kThreads) dst[i] = src[i];
 }
-__device__ __forceinline__ void copy_params_n(float* dst, const float* src, int n, int tid, int nthreads) {
-  for (int i = tid; i < n; i += nthreads) dst[i] = src[i];
-}
+
 
 #define AMUSE_PROF(slot)                                     \
   do {                                                       \
@@ -643,404 +639,6 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   cluster_sync_all();   // nobody leaves while a peer could still address its shared memory
 }
 
-// ================================================================= dual-group variant (2 clips / cluster)
-// Same algorithm, different schedule: the CTA runs TWO independent warp groups (4 warps each), one
-// clip per group, plus one TMA producer warp.  The two clips are independent dependency chains, so
-// whenever one group sits in a latency-bound phase (exchange wait, LayerNorm shuffles, K-split
-// fold, group barrier) the other group's FFMA2 stream fills the issue slots.  Groups synchronise
-// internally with named barriers (bar.sync id, 128) and share the weight ring: a ring slot is
-// refilled once BOTH groups have arrived on its "consumed" mbarrier.
-namespace dual {
-
-constexpr int kGroupThreads = 128;
-constexpr int kThreads2 = 2 * kGroupThreads + 32;   // + producer warp
-constexpr int kRows = 5, kKS = 4;
-// per-group shared memory (floats)
-constexpr int gXs = 0;
-constexpr int gSK = gXs + kRows * 128;
-constexpr int gPs = gSK + 4 * kRows * 128;           // [2 parity][3 peers][5][128]
-constexpr int kPsG = 3 * kRows * 128;
-constexpr int gQKV = gPs + 2 * kPsG;                 // [5][100] (+ Oh [5][36]); Hs [5][128] aliases both
-constexpr int gOh = gQKV + kRows * kQkvLd;
-constexpr int gRED = gOh + kRows * kOhLd;            // [4][5][128]
-constexpr int gCs = gRED + kKS * kRows * 128;        // [3][128]
-constexpr int gZs = gCs + 3 * 128;
-constexpr int gEs = gZs + 128;
-constexpr int gTemb = gEs + 128;
-constexpr int gBqkv = gTemb + 128;
-constexpr int gTail = gBqkv + 96;
-constexpr int kGroupFloats = gTail + kTileTail;
-static_assert(kRows * kQkvLd + kRows * kOhLd >= kRows * 128, "Hs aliases q|k|v + Oh");
-static_assert(kGroupFloats % 4 == 0, "group block must keep 16-B alignment");
-constexpr int oShared = 2 * kGroupFloats;            // pe01 [256] | final norm [256]
-constexpr int oBars = oShared + 512;                 // full[2] consumed[2] xbar[2][2]
-constexpr int kSmemFloats2 = 2 * kWBufFloats + oBars + 16;
-static_assert(kSmemFloats2 * 4 <= 232448, "exceeds the 227 KB shared-memory limit of sm_100");
-
-__device__ __forceinline__ void gsync(int g) {
-  asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(kGroupThreads) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads2, 1)
-    denoise_loop_dual_kernel(const Params p) {
-  extern __shared__ __align__(128) float smem_raw[];
-  float* const act = smem_raw + 2 * kWBufFloats;
-  uint64_t* const bars = reinterpret_cast<uint64_t*>(act + oBars);
-  uint64_t* const full = bars;            // [2] weight tile landed
-  uint64_t* const consumed = bars + 2;    // [2] weight tile read by every active group
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t rank = cluster_ctarank();
-  const int cid = static_cast<int>(cluster_id_x());
-  const int T = p.T;
-  const int s_base = cid * 2;
-  const int S = min(2, p.B - s_base);     // active groups (clips) of this cluster
-  const uint32_t total = static_cast<uint32_t>(p.n_steps) * kTilesPerStep;
-  const float* blob = p.blob + static_cast<size_t>(rank) * kBlobRankFloats;
-
-  for (int i = tid; i < oBars; i += kThreads2) act[i] = 0.f;
-  if (tid == 0) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
-    mbar_init(&consumed[0], S);
-    mbar_init(&consumed[1], S);
-    for (int i = 0; i < 4; ++i) mbar_init(bars + 4 + i, 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  for (int i = tid; i < 256; i += kThreads2) {
-    act[oShared + i] = p.pe01[i];
-    act[oShared + 256 + i] = p.final_norm[i];
-  }
-  __syncthreads();
-  cluster_sync_all();   // peers resident, zero-filled, mbarriers initialised
-
-  auto issue_tile = [&](uint32_t n) {
-    int off, cnt;
-    tile_info(static_cast<int>(n % kTilesPerStep), off, cnt);
-    mbar_arrive_expect_tx(&full[n & 1], static_cast<uint32_t>(cnt) * 4u);
-    bulk_g2s(smem_raw + (n & 1) * kWBufFloats, blob + off, static_cast<uint32_t>(cnt) * 4u, &full[n & 1]);
-  };
-
-  if (warp == 8) {
-    // ===================== TMA producer warp =====================
-    if (lane == 0) {
-      issue_tile(0);
-      if (total > 1) issue_tile(1);
-      for (uint32_t n = 2; n < total; ++n) {
-        mbar_wait(&consumed[n & 1], ((n >> 1) - 1) & 1);   // previous occupant of the slot read by all groups
-        issue_tile(n);
-      }
-    }
-  } else if ((warp >> 2) < S) {
-    // ===================== one clip per warp group =====================
-    const int g = warp >> 2, gw = warp & 3, gt = tid & 127;
-    float* const G = act + g * kGroupFloats;
-    float* const Xs = G + gXs;
-    float* const SK = G + gSK;
-    float* const QKVs = G + gQKV;
-    float* const Oh = G + gOh;
-    float* const Hs = G + gQKV;
-    float* const RED = G + gRED;
-    float* const Cs = G + gCs;
-    float* const zs = G + gZs;
-    float* const Es = G + gEs;
-    float* const tembs = G + gTemb;
-    float* const par_bqkv = G + gBqkv;
-    float* const par_tail = G + gTail;
-    const float* const pe01 = act + oShared;
-    const float* const fn = act + oShared + 256;
-    uint64_t* const xbar = bars + 4 + 2 * g;
-    const int clip = s_base + g;
-    const int ks = gw;                                   // GEMM role: K slice (one row block of 5 rows)
-    const int row0 = gw, row1 = gw + 4;                  // epilogue role: rows gw and (warp 0 only) 4
-    const bool own1 = row1 < kRows;
-    constexpr int kArmTid = 96;                          // warp 3 lane 0: the warp with the least epilogue work
-
-    for (int i = gt; i < 3 * 128; i += kGroupThreads) Cs[i] = p.cond[static_cast<size_t>(clip) * 384 + i];
-    zs[gt] = p.latents0[static_cast<size_t>(clip) * 128 + gt];
-    curandStatePhilox4_32_10_t rng;
-    const bool use_rng = (p.step_noise == nullptr);
-    if (use_rng) curand_init(p.seed, p.seed_elem_base + static_cast<unsigned long long>(clip) * 128ull + gt, 0, &rng);
-    float temb_next = __ldg(p.temb + gt);
-    float coef_next[5];
-#pragma unroll
-    for (int q = 0; q < 5; ++q) coef_next[q] = __ldg(p.coef + q);
-    float noise_next = use_rng ? 0.f : __ldg(p.step_noise + static_cast<size_t>(clip) * 128 + gt);
-    uint32_t wg = 0;    // weight tile sequence number
-    uint32_t xe = 0;    // exchange sequence number
-    gsync(g);
-    // Phase-offset the two groups by about half a stage: they do identical work, so without an offset
-    // they stay in lockstep (both in the FMA/LSU-bound GEMM loop, then both in the latency-bound
-    // epilogue) and nothing overlaps.  The offset persists: nothing in the protocol re-aligns them.
-    if (g == 1) {
-      const long long t0 = clock64();
-      const long long d = p.group_skew_cycles;
-      while (clock64() - t0 < d) {
-      }
-    }
-
-    auto acquire = [&]() -> const float* {
-      mbar_wait(&full[wg & 1], (wg >> 1) & 1);
-      return smem_raw + (wg & 1) * kWBufFloats;
-    };
-    auto release = [&]() {   // call after a gsync that follows the last read of tile wg
-      if (gt == kArmTid) mbar_arrive(&consumed[wg & 1]);
-      ++wg;
-    };
-    auto send_row_g = [&](int row, const Row4& v) {
-      float* ps = G + gPs + (xe & 1) * kPsG;
-#pragma unroll
-      for (uint32_t d = 1; d < kCluster; ++d) {
-        const uint32_t peer = (rank + d) & (kCluster - 1);
-        const uint32_t slot = (rank < peer) ? rank : rank - 1;
-        const uint32_t dst = map_to_rank(ps + (slot * kRows + row) * 128 + 2 * lane, peer);
-        const uint32_t rbar = map_to_rank(&xbar[xe & 1], peer);
-        st_async_f2(dst, v.lo, rbar);
-        st_async_f2(dst + 64 * 4, v.hi, rbar);
-      }
-    };
-    // K-split partial -> st.async exchange -> sum + bias [+ residual] [+ LayerNorm] -> Xs [, skip stack]
-    auto exchange_epilogue = [&](const float* bias, const float* resid, const float* lnp, float* dst2) {
-      Row4 v[2];
-      v[0] = gather4<kRows, kKS>(RED, row0, lane);
-      send_row_g(row0, v[0]);
-      v[1] = v[0];
-      if (own1) {
-        v[1] = gather4<kRows, kKS>(RED, row1, lane);
-        send_row_g(row1, v[1]);
-      }
-      const Row4 b = ld_row4(bias, lane);
-      v[0] = add4(v[0], b);
-      if (resid) v[0] = add4(v[0], ld_row4(resid + row0 * 128, lane));
-      if (own1) {
-        v[1] = add4(v[1], b);
-        if (resid) v[1] = add4(v[1], ld_row4(resid + row1 * 128, lane));
-      }
-      mbar_wait(&xbar[xe & 1], (xe >> 1) & 1);
-      const float* ps = G + gPs + (xe & 1) * kPsG;
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        v[0] = add4(v[0], ld_row4(ps + (q * kRows + row0) * 128, lane));
-        if (own1) v[1] = add4(v[1], ld_row4(ps + (q * kRows + row1) * 128, lane));
-      }
-      if (lnp) layernorm2(v, lnp, lane);
-      st_row4(Xs + row0 * 128, lane, v[0]);
-      if (dst2) st_row4(dst2 + row0 * 128, lane, v[0]);
-      if (own1) {
-        st_row4(Xs + row1 * 128, lane, v[1]);
-        if (dst2) st_row4(dst2 + row1 * 128, lane, v[1]);
-      }
-      ++xe;
-      gsync(g);
-    };
-    auto arm = [&]() {
-      if (gt == kArmTid) mbar_arrive_expect_tx(&xbar[xe & 1], 3u * kRows * 128u * 4u);
-    };
-
-    for (int step = 0; step < p.n_steps; ++step) {
-      const bool do_prof = (p.prof != nullptr) && cid == 0 && rank == 0 && g == 0 && step == p.prof_step;
-      if (do_prof && gt == 0) p.prof[0] = clock64();
-      float coef[5];
-#pragma unroll
-      for (int q = 0; q < 5; ++q) coef[q] = coef_next[q];
-      const float noise = noise_next;
-      tembs[gt] = temb_next;
-      if (step + 1 < p.n_steps) {
-        temb_next = __ldg(p.temb + static_cast<size_t>(step + 1) * 128 + gt);
-#pragma unroll
-        for (int q = 0; q < 5; ++q) coef_next[q] = __ldg(p.coef + static_cast<size_t>(step + 1) * 5 + q);
-        if (!use_rng) noise_next = __ldg(p.step_noise + (static_cast<size_t>(step + 1) * p.B + clip) * 128 + gt);
-      }
-      gsync(g);
-      // token rows: z + pe0 | time token + pe1 | condition tokens (+pe, precomputed)
-      for (int idx = gt; idx < T * 32; idx += kGroupThreads) {
-        const int r = idx >> 5, c4 = (idx & 31) * 4;
-        float4 v;
-        if (r == 0)
-          v = add4(*reinterpret_cast<const float4*>(zs + c4), *reinterpret_cast<const float4*>(pe01 + c4));
-        else if (r == 1)
-          v = add4(*reinterpret_cast<const float4*>(tembs + c4), *reinterpret_cast<const float4*>(pe01 + 128 + c4));
-        else
-          v = *reinterpret_cast<const float4*>(Cs + (r - 2) * 128 + c4);
-        *reinterpret_cast<float4*>(Xs + r * 128 + c4) = v;
-      }
-      gsync(g);
-      if (do_prof && gt == 0) p.prof[1] = clock64();
-
-      for (int layer = 0; layer < kLayers; ++layer) {
-        if (layer >= 5) {   // x = Linear(256->128)(cat(x, xs.pop())), K-split 64 per CTA
-          const float* wt = acquire();
-          arm();
-          copy_params_n(par_tail, wt + 64 * 128, 128, gt, kGroupThreads);
-          const float* src = (rank < 2) ? (Xs + rank * 64) : (SK + (8 - layer) * kRows * 128 + (rank - 2) * 64);
-          float acc[5][4];
-          gemm5<128, 4, (64 / kKS) / 4>(src + ks * (64 / kKS), 128, wt + (ks * (32 / kKS)) * 256 + lane * 2, acc);
-          park4<kRows>(RED, 0, ks, lane, acc);
-          gsync(g);
-          release();
-          exchange_epilogue(par_tail, nullptr, nullptr, nullptr);
-        }
-        if (do_prof && gt == 0) p.prof[2 + layer * 10 + 0] = clock64();
-        {   // QKV of my head
-          const float* wt = acquire();
-          copy_params_n(par_bqkv, wt + 128 * 96, 96, gt, kGroupThreads);
-          float acc[5][3];
-          gemm5<96, 3, (128 / kKS) / 4>(Xs + ks * (128 / kKS), 128, wt + (ks * (64 / kKS)) * 192 + lane * 2, acc);
-          {
-            float* dst = RED + (ks * kRows) * 96 + lane;
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-              dst[i * 96] = acc[i][0];
-              dst[i * 96 + 32] = acc[i][1];
-              dst[i * 96 + 64] = acc[i][2];
-            }
-          }
-          gsync(g);
-          release();
-#pragma unroll
-          for (int o = 0; o < 2; ++o) {
-            const int row = o ? row1 : row0;
-            if (o == 0 || own1) {
-              float q = par_bqkv[lane], k = par_bqkv[32 + lane], v = par_bqkv[64 + lane];
-#pragma unroll
-              for (int c = 0; c < kKS; ++c) {
-                const float* src = RED + ((c * kRows + row) * 96) + lane;
-                q += src[0];
-                k += src[32];
-                v += src[64];
-              }
-              float* dst = QKVs + row * kQkvLd + lane;
-              dst[0] = q * 0.17677669529663687f;
-              dst[32] = k;
-              dst[64] = v;
-            }
-          }
-          gsync(g);
-        }
-        if (do_prof && gt == 0) p.prof[2 + layer * 10 + 1] = clock64();
-        if (gw == 0) {   // T x T attention of my head for this clip
-          const float* base = QKVs;
-          const int i = (lane < 25) ? lane / 5 : 0, j = lane % 5;
-          const bool valid = (lane < 25) && (i < T) && (j < T);
-          const int ic = valid ? i : 0, jc = valid ? j : 0;
-          float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
-          const float4* qv = reinterpret_cast<const float4*>(base + ic * kQkvLd);
-          const float4* kv = reinterpret_cast<const float4*>(base + jc * kQkvLd + 32);
-#pragma unroll
-          for (int c = 0; c < 8; c += 2) {
-            const float4 a = qv[c], b = kv[c], a2 = qv[c + 1], b2 = kv[c + 1];
-            p0 = fmaf(a.x, b.x, p0);
-            p1 = fmaf(a.y, b.y, p1);
-            p2 = fmaf(a.z, b.z, p2);
-            p3 = fmaf(a.w, b.w, p3);
-            p0 = fmaf(a2.x, b2.x, p0);
-            p1 = fmaf(a2.y, b2.y, p1);
-            p2 = fmaf(a2.z, b2.z, p2);
-            p3 = fmaf(a2.w, b2.w, p3);
-          }
-          const float sc = valid ? ((p0 + p1) + (p2 + p3)) : -INFINITY;
-          float sj[5];
-#pragma unroll
-          for (int jj = 0; jj < 5; ++jj) sj[jj] = __shfl_sync(0xffffffffu, sc, i * 5 + jj);
-          const float m = fmaxf(fmaxf(fmaxf(sj[0], sj[1]), fmaxf(sj[2], sj[3])), sj[4]);
-          const float e = valid ? expf(sc - m) : 0.f;
-          float ej[5];
-#pragma unroll
-          for (int jj = 0; jj < 5; ++jj) ej[jj] = __shfl_sync(0xffffffffu, e, i * 5 + jj);
-          const float sum = (ej[0] + ej[1]) + (ej[2] + ej[3]) + ej[4];
-          const float pr = valid ? e / sum : 0.f;
-          float vj[5];
-#pragma unroll
-          for (int jj = 0; jj < 5; ++jj) vj[jj] = (jj < T) ? base[jj * kQkvLd + 64 + lane] : 0.f;
-#pragma unroll
-          for (int ii = 0; ii < 5; ++ii) {
-            float o = 0.f;
-#pragma unroll
-            for (int jj = 0; jj < 5; ++jj) o = fmaf(__shfl_sync(0xffffffffu, pr, ii * 5 + jj), vj[jj], o);
-            if (ii < T) Oh[ii * kOhLd + lane] = o;
-          }
-        }
-        gsync(g);
-        if (do_prof && gt == 0) p.prof[2 + layer * 10 + 2] = clock64();
-        {   // out_proj, K-split by head -> exchange -> sum + LN1
-          const float* wt = acquire();
-          arm();
-          copy_params_n(par_tail, wt + 32 * 128, kTileTail, gt, kGroupThreads);
-          float acc[5][4];
-          gemm5<128, 4, (32 / kKS) / 4>(Oh + ks * (32 / kKS), kOhLd, wt + (ks * (16 / kKS)) * 256 + lane * 2, acc);
-          park4<kRows>(RED, 0, ks, lane, acc);
-          gsync(g);
-          release();
-          exchange_epilogue(par_tail, Xs, par_tail + 128, nullptr);
-        }
-        if (do_prof && gt == 0) p.prof[2 + layer * 10 + 4] = clock64();
-        {   // FFN1 + erf-GELU
-          const float* wt = acquire();
-          copy_params_n(par_tail, wt + 128 * 128, 128, gt, kGroupThreads);
-          float acc[5][4];
-          gemm5<128, 4, (128 / kKS) / 4>(Xs + ks * (128 / kKS), 128, wt + (ks * (64 / kKS)) * 256 + lane * 2, acc);
-          park4<kRows>(RED, 0, ks, lane, acc);
-          gsync(g);
-          release();
-          const Row4 b = ld_row4(par_tail, lane);
-#pragma unroll
-          for (int o = 0; o < 2; ++o) {
-            const int row = o ? row1 : row0;
-            if (o == 0 || own1) {
-              Row4 v = add4(gather4<kRows, kKS>(RED, row, lane), b);
-              v.lo = make_float2(gelu_erf(v.lo.x), gelu_erf(v.lo.y));
-              v.hi = make_float2(gelu_erf(v.hi.x), gelu_erf(v.hi.y));
-              st_row4(Hs + row * 128, lane, v);
-            }
-          }
-          gsync(g);
-        }
-        if (do_prof && gt == 0) p.prof[2 + layer * 10 + 5] = clock64();
-        {   // FFN2, K-split -> exchange -> sum + LN2
-          const float* wt = acquire();
-          arm();
-          copy_params_n(par_tail, wt + 128 * 128, kTileTail, gt, kGroupThreads);
-          float acc[5][4];
-          gemm5<128, 4, (128 / kKS) / 4>(Hs + ks * (128 / kKS), 128, wt + (ks * (64 / kKS)) * 256 + lane * 2, acc);
-          park4<kRows>(RED, 0, ks, lane, acc);
-          gsync(g);
-          release();
-          exchange_epilogue(par_tail, Xs, par_tail + 128, (layer < 4) ? (SK + layer * kRows * 128) : nullptr);
-        }
-        if (do_prof && gt == 0) p.prof[2 + layer * 10 + 7] = clock64();
-      }   // layers
-
-      if (gw == 0) {   // encoder.norm on token 0 -> eps
-        const float4 v = *reinterpret_cast<const float4*>(Xs + lane * 4);
-        const float4 gg = *reinterpret_cast<const float4*>(fn + lane * 4);
-        const float4 bb = *reinterpret_cast<const float4*>(fn + 128 + lane * 4);
-        *reinterpret_cast<float4*>(Es + lane * 4) = warp_layernorm128(v, gg, bb);
-      }
-      gsync(g);
-      {   // scheduler step (K2): one latent element per thread
-        const float x = zs[gt], e = Es[gt];
-        float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(coef[1], e)), coef[0]);
-        if (p.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
-        float out = __fadd_rn(__fmul_rn(coef[2], x0), __fmul_rn(coef[3], p.dir_uses_eps ? e : x));
-        if (coef[4] != 0.f) {
-          const float zn = use_rng ? curand_normal(&rng) : noise;
-          out = __fadd_rn(out, __fmul_rn(coef[4], zn));
-        }
-        zs[gt] = out;
-      }
-      gsync(g);
-      if (do_prof && gt == 0) p.prof[2 + kLayers * 10] = clock64();
-    }   // steps
-    if (rank == 0) p.latents_out[static_cast<size_t>(clip) * 128 + gt] = zs[gt];
-  }
-  cluster_sync_all();   // nobody leaves while a peer could still address its shared memory
-}
-
-}  // namespace dual
-
 size_t smem_bytes() { return static_cast<size_t>(kSmemFloats) * sizeof(float); }
 
 cudaError_t launch(const Params& p, cudaStream_t stream) {
@@ -1056,21 +654,10 @@ cudaError_t launch(const Params& p, cudaStream_t stream) {
   }
   if (p.S < 1 || p.S > kSMax) return cudaErrorInvalidValue;
   const int n_clusters = (p.B + p.S - 1) / p.S;
-  static const bool single_group = (getenv("AMUSE_LOOP_SINGLE_GROUP") != nullptr);   // A/B switch for measurements
-  if (p.S == 1) {
+  if (p.S == 1)
     denoise_loop_kernel<1><<<dim3(n_clusters * kCluster), dim3(kThreads), smem_bytes(), stream>>>(p);
-  } else if (single_group) {
+  else
     denoise_loop_kernel<2><<<dim3(n_clusters * kCluster), dim3(kThreads), smem_bytes(), stream>>>(p);
-  } else {
-    static bool configured2 = false;
-    if (!configured2) {
-      cudaError_t e = cudaFuncSetAttribute(dual::denoise_loop_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           dual::kSmemFloats2 * 4);
-      if (e != cudaSuccess) return e;
-      configured2 = true;
-    }
-    dual::denoise_loop_dual_kernel<<<dim3(n_clusters * kCluster), dim3(dual::kThreads2), dual::kSmemFloats2 * 4, stream>>>(p);
-  }
   return cudaGetLastError();
 }
 

@@ -69,7 +69,6 @@ struct Params {
   unsigned long long seed;   // Philox seed when step_noise == nullptr and sigma > 0
   unsigned long long seed_elem_base;   // global index of this launch's first latent element (multi-GPU shards)
   int prof_step;
-  int group_skew_cycles;     // dual-group kernel: initial phase offset of the second warp group
 };
 
 size_t smem_bytes();

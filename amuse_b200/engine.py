@@ -186,6 +186,17 @@ class Engine:
                 _ptr(noise), seed, _ptr(poses), _ptr(trans), self._stream()))
         return {"poses": poses, "trans": trans}
 
+    def fbank(self, wave: torch.Tensor, norm_mean: float = -9.173025, norm_std: float = 5.062332) -> torch.Tensor:
+        """[B, n_samples] 16 kHz mono waveforms -> [B, 1024, 128] normalised Kaldi log-mel filterbank."""
+        x = self._dev(wave)
+        if x.dim() != 2:
+            raise ValueError("wave must be [B, n_samples]")
+        B, n = x.shape
+        out = torch.empty(B, 1024, 128, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.amuse_fbank(self._h, B, n, _ptr(x), norm_mean, norm_std, _ptr(out), self._stream()))
+        return out
+
     def ast_features(self, fbank: torch.Tensor):
         B = fbank.shape[0]
         x = self._dev(fbank, (B, 1024, 128))

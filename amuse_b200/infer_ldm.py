@@ -73,6 +73,7 @@ class PretrainedLPDM_v1:
 
     # engine-side knobs that the reference hard-wires; defaults reproduce the reference
     sampler = "ddim"               # diffusers.DDIMScheduler (infer_ldm.py:116); "ddpm" = ancestral sampler
+    device_fbank = True            # filterbank on the GPU; False = torchaudio on the host, as the reference
 
     def __init__(self, base_prior, base_con_ae=None, base_emo_ae=None, base_audio_ae=None):
         self.base_vae = base_prior
@@ -244,7 +245,10 @@ class PretrainedLPDM_v1:
         """[C, N] waveform (assumed 16 kHz) -> (con, emo, sty), each [1, 256] on ``self.device``."""
         if not getattr(self, "has_ast", False):
             raise RuntimeError("AST encoder weights were not loaded")
-        fbank = self._fbank(sliced_chunk)
+        if self.device_fbank:     # Kaldi fbank + pad + normalise on the GPU (amuse_fbank); channel 0 like kaldi's channel=-1
+            fbank = self.engine.fbank(sliced_chunk[:1].to(self.device), self.norm_mean, self.norm_std)[0]
+        else:                     # the reference's host path (torchaudio on the CPU)
+            fbank = self._fbank(sliced_chunk)
         # (the reference raises here when more than one GPU is visible, infer_pretrained_ast_evp.py:45;
         #  this engine is one-process-per-GPU and has no such restriction)
         con, emo, sty = self.engine.ast_features(fbank.unsqueeze(0))
