@@ -273,6 +273,7 @@ def run_ours(args, rank, world, local_rank):
         poses = dev_step()
         torch.cuda.synchronize(dev)
         bufs = [torch.empty_like(poses) for _ in range(world)] if rank == 0 else None
+        dist.gather(poses, bufs, dst=0)          # warm-up (NCCL lazy init)
         barrier()
         g0 = time.perf_counter()
         dist.gather(poses, bufs, dst=0)
@@ -309,6 +310,33 @@ def run_ours(args, rank, world, local_rank):
     t_cpu_full = (t_cpu - t_cdec) * (N_STEPS / cs) + t_cdec
     cpu_value = B * FRAMES / t_cpu_full
 
+    # PyTorch-eager on the SAME GPU (the reference's own execution model: one ATen launch per op), via
+    # the oracle port moved to the device -- a reported baseline only (north_star: ">= 10x the
+    # reference single-GPU infer_gesture wall-clock"); bounded sample, scaled like the CPU one.
+    eager = None
+    try:
+        den_g = {k: v.to(dev) for k, v in den_c.items()}
+        vae_g = {k: v.to(dev) for k, v in vae_c.items()}
+        gi = [t.to(dev) for t in synth_inputs(B)]
+        es = 20
+        gn = torch.randn(es, B, 128, device=dev)
+        from oracle import lpdm_ref as R2
+        def eager_run(n):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            R2.diffusion_backward(den_g, vae_g, gi[0], gi[1], gi[2], gi[3], n_steps=n, sampler=SAMPLER, step_noise=gn[:n])
+            torch.cuda.synchronize(dev)
+            return time.perf_counter() - t0
+        eager_run(2)
+        t_e = eager_run(es)
+        t_d = eager_run(1)            # ~ decode + one step
+        per_step = max((t_e - t_d) / (es - 1), 1e-9)
+        t_eager_full = per_step * N_STEPS + max(t_d - per_step, 0.0)
+        eager = {"value": B * FRAMES / t_eager_full, "unit": "frames/s", "kind": "oracle port in PyTorch eager on cuda",
+                 "sample": f"{es} of {N_STEPS} denoiser steps timed and scaled, plus one decode", "ms_per_denoiser_step": per_step * 1e3}
+    except Exception as e:  # noqa
+        log("[bench] eager-GPU baseline skipped:", repr(e))
+
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": t_total / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -328,6 +356,7 @@ def run_ours(args, rank, world, local_rank):
         "cpu_baseline": {"value": cpu_value, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"B={B}: {cs} of {N_STEPS} denoiser steps timed and scaled x{N_STEPS // cs}, plus one full decode; "
                                    f"thread count auto-picked from a probe (host has {os.cpu_count()} logical CPUs)"},
+        "eager_gpu_baseline": eager,
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

@@ -128,7 +128,7 @@ def skip_decoder(x: Tensor, mem: Tensor, sd: SD, p: str) -> Tensor:
 # --------------------------------------------------------------------------- denoiser
 def time_token(sd: SD, t: Tensor, dtype) -> Tensor:
     """``Timesteps`` + ``TimestepEmbedding`` (embeddings.py:288-322): Linear-SiLU-Linear."""
-    e = timestep_sinusoid(t, 256, True, 0.0, dtype)
+    e = timestep_sinusoid(t, 256, True, 0.0, dtype).to(sd["time_embedding.linear_1.weight"].device)
     e = F.linear(e, sd["time_embedding.linear_1.weight"], sd["time_embedding.linear_1.bias"])
     e = F.silu(e)
     return F.linear(e, sd["time_embedding.linear_2.weight"], sd["time_embedding.linear_2.bias"])
@@ -268,7 +268,7 @@ def vae_decode(sd: SD, z: Tensor, nframes: int = 300) -> Tensor:
     pe_type mld, all lengths = nframes (mask all-true => the zeroing at :274 is a no-op).
     ``z`` [B,128] (one latent token per clip) -> feats [B,nframes,333]."""
     B = z.shape[0]
-    q = torch.zeros(B, nframes, z.shape[-1], dtype=z.dtype) + sd["query_pos_decoder.pe"][:nframes, 0, :][None]
+    q = torch.zeros(B, nframes, z.shape[-1], dtype=z.dtype, device=z.device) + sd["query_pos_decoder.pe"][:nframes, 0, :][None]
     x = skip_decoder(q, z[:, None, :], sd, "decoder")
     return F.linear(x, sd["final_layer.weight"], sd["final_layer.bias"])
 
