@@ -1,0 +1,314 @@
+// AST self-attention on tcgen05 / TMEM / TMA with 3xTF32 accuracy (see ast_attn.cuh).
+//
+// One CTA = one (clip, head, block of 256 queries) = two 128-row query tiles that share every
+// key/value tile (halves the L2 -> SM traffic per MMA; with one tile per CTA the K/V stream alone
+// would need ~42 B/clk/SM, the whole L2 fabric).  Key/value tiles are 32 keys wide.
+//   warp 0      TMA producer: Q_hi/Q_lo of both query tiles once (128 KB), then per key tile
+//               K_hi, K_lo (32 x 64) and V^T_hi, V^T_lo (64 x 32) into a 3-stage ring (32 KB / stage)
+//   warp 1      TMEM allocation + MMA issue (one lane):
+//                 S_t  = Q_t . K^T        A, B from shared memory   3 x 8 tcgen05.mma  M128 N32 K8
+//                 O_t += P_t . V          A = P_t from TMEM          3 x 4 tcgen05.mma  M128 N64 K8
+//               software-pipelined  S_0(j+1) S_1(j+1) PV_0(j) PV_1(j)  so the softmax of tile j
+//               overlaps the score MMAs of tile j+1
+//   warps 2-5   softmax of query tile 0, warps 6-9 of query tile 1: one query row per thread
+//               (TMEM lane = row): tcgen05.ld S -> online softmax in the log2 domain (q is pre-scaled
+//               by 64^-0.5 * log2 e) -> P split into TF32 hi/lo planes -> tcgen05.st into TMEM.
+//               The running maximum is only raised (and O rescaled through tcgen05.ld/st) when it
+//               grows by more than 2^8 -- exact after the final division by the row sum.
+// 3xTF32: x = hi + lo; x.y ~= hi.hi + lo.hi + hi.lo with fp32 accumulation in TMEM.
+#include "ast_attn.cuh"
+
+#include "tc_gemm.cuh"
+#include "tc_ptx.cuh"
+
+namespace amuse {
+namespace attn {
+
+namespace {
+
+using namespace tcp;
+
+constexpr int kThreads = 320;
+constexpr int kKT = 32;                         // keys per tile
+constexpr int kNT = (kTok + kKT - 1) / kKT;     // 38 key tiles
+constexpr int kStages = 3;
+constexpr int kQTile = 128 * 32 * 4;            // one 128-row x 32-column box: 16 KB
+constexpr int kQBytes = 8 * kQTile;             // 2 tiles x {hi, lo} x 2 column halves
+constexpr int kKBox = kKT * 32 * 4;             // 32 keys x 32 columns: 4 KB
+constexpr int kVBox = kHD * kKT * 4;            // 64 d x 32 keys: 8 KB
+constexpr int kStageBytes = 4 * kKBox + 2 * kVBox;   // 32 KB
+constexpr int kBarOff = kQBytes + kStages * kStageBytes;
+constexpr int kSmemBytes = kBarOff + 256 + 1024;
+static_assert(kSmemBytes <= 232448, "exceeds the 227 KB shared-memory limit of sm_100");
+
+// TMEM columns
+constexpr uint32_t kColO = 0;      // O_t : [t*64, t*64+64)
+constexpr uint32_t kColS = 128;    // S_t : [128 + t*32, +32)
+constexpr uint32_t kColP = 192;    // P_t : hi [192 + t*64, +32), lo [+32, +64)
+constexpr int kTmemCols = 512;
+
+constexpr uint32_t kIdescS = idesc_tf32(128, kKT);
+constexpr uint32_t kIdescPV = idesc_tf32(128, kHD);
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1)
+    ast_attention_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ CUtensorMap tmQ_lo,
+                         const __grid_constant__ CUtensorMap tmK_hi, const __grid_constant__ CUtensorMap tmK_lo,
+                         const __grid_constant__ CUtensorMap tmV_hi, const __grid_constant__ CUtensorMap tmV_lo,
+                         float* __restrict__ o_hi, float* __restrict__ o_lo) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);
+  uint64_t* q_full = bars;              // [1]
+  uint64_t* kv_full = bars + 1;         // [3]
+  uint64_t* kv_empty = bars + 4;        // [3]
+  uint64_t* s_full = bars + 7;          // [2]  MMA -> softmax t: S_t(j) complete
+  uint64_t* s_free = bars + 9;          // [2]  softmax t -> MMA: S_t(j) is in registers
+  uint64_t* p_ready = bars + 11;        // [2]  softmax t -> MMA: P_t(j) stored (and O_t rescaled)
+  uint64_t* pv_done = bars + 13;        // [2]  MMA -> softmax t: O_t += P_t(j) V(j) complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qblk = blockIdx.x, head = blockIdx.y, clip = blockIdx.z;
+  const int bh = clip * kHeads + head;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmQ_hi);
+    prefetch_tmap(&tmQ_lo);
+    prefetch_tmap(&tmK_hi);
+    prefetch_tmap(&tmK_lo);
+    prefetch_tmap(&tmV_hi);
+    prefetch_tmap(&tmV_lo);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&s_free[t], 4);
+      mbar_init(&p_ready[t], 4);
+      mbar_init(&pv_done[t], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      const int qrow = bh * kTokP + qblk * 256;
+      mbar_arrive_expect_tx(q_full, kQBytes);
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          tma_load_2d(smem + ((t * 2 + 0) * 2 + kb) * kQTile, &tmQ_hi, q_full, kb * 32, qrow + t * 128);
+          tma_load_2d(smem + ((t * 2 + 1) * 2 + kb) * kQTile, &tmQ_lo, q_full, kb * 32, qrow + t * 128);
+        }
+      const int krow = bh * kTokP, vrow = bh * kHD;
+      for (int j = 0; j < kNT; ++j) {
+        const int s = j % kStages;
+        mbar_wait(&kv_empty[s], ((j / kStages) & 1) ^ 1);
+        uint8_t* st = smem + kQBytes + s * kStageBytes;
+        mbar_arrive_expect_tx(&kv_full[s], kStageBytes);
+        tma_load_2d(st + 0 * kKBox, &tmK_hi, &kv_full[s], 0, krow + j * kKT);
+        tma_load_2d(st + 1 * kKBox, &tmK_hi, &kv_full[s], 32, krow + j * kKT);
+        tma_load_2d(st + 2 * kKBox, &tmK_lo, &kv_full[s], 0, krow + j * kKT);
+        tma_load_2d(st + 3 * kKBox, &tmK_lo, &kv_full[s], 32, krow + j * kKT);
+        tma_load_2d(st + 4 * kKBox, &tmV_hi, &kv_full[s], j * kKT, vrow);
+        tma_load_2d(st + 4 * kKBox + kVBox, &tmV_lo, &kv_full[s], j * kKT, vrow);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      // descriptors differ only in the 14-bit start-address field (bytes >> 4); every operand offset is
+      // a compile-time constant from the 1024-B aligned base, so they are formed by one 64-bit add
+      const uint64_t d0 = umma_desc(smem_u32(smem));
+      auto issue_S = [&](int t, int s) {
+        const uint64_t q0 = d0 + ((t * 4 * kQTile) >> 4);
+        const uint64_t k0 = d0 + ((kQBytes + s * kStageBytes) >> 4);
+        const uint32_t dS = tmem_base + kColS + t * kKT;
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t a_hi = q0 + ((kb * kQTile + k * 32) >> 4);
+            const uint64_t a_lo = q0 + (((2 + kb) * kQTile + k * 32) >> 4);
+            const uint64_t b_hi = k0 + ((kb * kKBox + k * 32) >> 4);
+            const uint64_t b_lo = k0 + (((2 + kb) * kKBox + k * 32) >> 4);
+            umma_tf32_ss(dS, a_hi, b_hi, kIdescS, (kb | k) ? 1u : 0u);
+            umma_tf32_ss(dS, a_lo, b_hi, kIdescS, 1u);
+            umma_tf32_ss(dS, a_hi, b_lo, kIdescS, 1u);
+          }
+        umma_commit(&s_full[t]);
+      };
+      auto issue_PV = [&](int t, int s, bool first) {
+        const uint64_t v0 = d0 + ((kQBytes + s * kStageBytes + 4 * kKBox) >> 4);
+        const uint32_t dO = tmem_base + kColO + t * kHD;
+        const uint32_t aP = tmem_base + kColP + t * 2 * kKT;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t b_hi = v0 + ((k * 32) >> 4);
+          const uint64_t b_lo = v0 + ((kVBox + k * 32) >> 4);
+          umma_tf32_ts(dO, aP + k * 8, b_hi, kIdescPV, (!first || k) ? 1u : 0u);
+          umma_tf32_ts(dO, aP + kKT + k * 8, b_hi, kIdescPV, 1u);
+          umma_tf32_ts(dO, aP + k * 8, b_lo, kIdescPV, 1u);
+        }
+        umma_commit(&pv_done[t]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_S(0, 0);
+      issue_S(1, 0);
+      for (int j = 0; j < kNT; ++j) {
+        const int s = j % kStages;
+        if (j + 1 < kNT) {
+          const int s1 = (j + 1) % kStages;
+          mbar_wait(&kv_full[s1], ((j + 1) / kStages) & 1);
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(&s_free[t], j & 1);
+            tc_fence_after();
+            issue_S(t, s1);
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&p_ready[t], j & 1);
+          tc_fence_after();
+          issue_PV(t, s, j == 0);
+        }
+        umma_commit(&kv_empty[s]);   // stage s is free once S(j) and PV(j) of both tiles have read it
+      }
+    }
+  } else {
+    // ===================== softmax / correction / epilogue =====================
+    const int t = (warp - 2) >> 2;          // query tile
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may address
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t aS = lane_base + kColS + t * kKT;
+    const uint32_t aP = lane_base + kColP + t * 2 * kKT;
+    const uint32_t aO = lane_base + kColO + t * kHD;
+    float m = 0.f, l = 0.f;
+    for (int j = 0; j < kNT; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      float sc[32];
+      tmem_ld32(aS, sc);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[t]);
+      if (j == kNT - 1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (j * kKT + i >= kTok) sc[i] = -INFINITY;
+      }
+      float mx = sc[0];
+#pragma unroll
+      for (int i = 1; i < 32; ++i) mx = fmaxf(mx, sc[i]);
+      const bool raise = (j == 0) || (mx > m + 8.0f);
+      const float m_use = raise ? mx : m;
+      float ph[32], pl[32], ls = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float p = ex2(sc[i] - m_use);
+        ls += p;
+        split_tf32(p, ph[i], pl[i]);
+      }
+      if (j > 0) {
+        mbar_wait(&pv_done[t], (j - 1) & 1);   // P_t buffer free, O_t quiescent
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, raise)) {
+          const float f = raise ? ex2(m - m_use) : 1.0f;
+          l *= f;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            float o[32];
+            tmem_ld32(aO + c * 32, o);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] *= f;
+            tmem_st32(aO + c * 32, o);
+          }
+        }
+      }
+      l += ls;
+      m = m_use;
+      tmem_st32(aP, ph);
+      tmem_st32(aP + kKT, pl);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[t]);
+    }
+    mbar_wait(&pv_done[t], (kNT - 1) & 1);
+    tc_fence_after();
+    const int tok = qblk * 256 + t * 128 + q * 32 + lane;
+    const float inv = 1.0f / l;
+    const size_t off = (static_cast<size_t>(clip) * kTok + (tok < kTok ? tok : 0)) * (kHeads * kHD) + head * kHD;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float o[32];
+      tmem_ld32(aO + c * 32, o);
+      if (tok < kTok) {
+        float4* dh = reinterpret_cast<float4*>(o_hi + off + c * 32);
+        float4* dl = reinterpret_cast<float4*>(o_lo + off + c * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 h, lo4;
+          split_tf32(o[i * 4 + 0] * inv, h.x, lo4.x);
+          split_tf32(o[i * 4 + 1] * inv, h.y, lo4.y);
+          split_tf32(o[i * 4 + 2] * inv, h.z, lo4.z);
+          split_tf32(o[i * 4 + 3] * inv, h.w, lo4.w);
+          dh[i] = h;
+          dl[i] = lo4;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+cudaError_t attention(const AttnArgs& a, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(ast_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (a.nb < 1) return cudaErrorInvalidValue;
+  CUtensorMap tm[6];
+  const int qk_rows = a.nb * kHeads * kTokP, v_rows = a.nb * kHeads * kHD;
+  cudaError_t e;
+  if ((e = tc::make_map_2d(&tm[0], a.q_hi, qk_rows, kHD, kHD, 128)) != cudaSuccess) return e;
+  if ((e = tc::make_map_2d(&tm[1], a.q_lo, qk_rows, kHD, kHD, 128)) != cudaSuccess) return e;
+  if ((e = tc::make_map_2d(&tm[2], a.k_hi, qk_rows, kHD, kHD, kKT)) != cudaSuccess) return e;
+  if ((e = tc::make_map_2d(&tm[3], a.k_lo, qk_rows, kHD, kHD, kKT)) != cudaSuccess) return e;
+  if ((e = tc::make_map_2d(&tm[4], a.vt_hi, v_rows, kTokP, kTokP, kHD)) != cudaSuccess) return e;
+  if ((e = tc::make_map_2d(&tm[5], a.vt_lo, v_rows, kTokP, kTokP, kHD)) != cudaSuccess) return e;
+  dim3 grid(kTokP / 256, kHeads, a.nb);
+  ast_attention_kernel<<<grid, kThreads, kSmemBytes, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], a.o_hi, a.o_lo);
+  return cudaGetLastError();
+}
+
+}  // namespace attn
+}  // namespace amuse

@@ -4,8 +4,9 @@
 //
 // All dense layers run on the tcgen05 3xTF32 GEMM (tc_gemm.cu): patch embedding as an im2col GEMM
 // (K = 256), qkv / proj / fc1 / fc2 with bias, q-scaling, erf-GELU and the residual add fused in the
-// epilogues.  Activations travel as TF32 hi/lo planes (value = hi + lo).  LayerNorm (eps 1e-6) and the
-// 1214-token attention (12 heads x 64) are fp32 CUDA-core kernels in this round.
+// epilogues.  Activations travel as TF32 hi/lo planes (value = hi + lo).  The 1214-token attention
+// (12 heads x 64) is the tcgen05 flash-attention kernel of ast_attn.cu, fed by per-head q / k / v^T
+// planes written straight from the qkv GEMM epilogue; LayerNorm (eps 1e-6) is an fp32 CUDA-core kernel.
 // The three branches share one im2col of the filterbank; clips are processed in chunks.
 #include "ast_kernels.cuh"
 
@@ -13,6 +14,7 @@
 #include <cstring>
 
 #include "../../include/amuse_b200.h"
+#include "ast_attn.cuh"
 #include "common.cuh"
 #include "tc_gemm.cuh"
 
@@ -56,7 +58,7 @@ struct Impl {
   int depth = 0;
   Branch br[3];   // con, emo, sty
   std::vector<float*> owned;
-  Buf P, tmp, X, Hn, QKV, O, Hid, pooled;
+  Buf P, tmp, X, Hn, Qp, Kp, Vp, O, Hid, pooled;
 };
 
 __device__ __forceinline__ void split2(float x, float& hi, float& lo) {
@@ -146,99 +148,6 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
     split2(v[i].w * rstd * gg.w + bb.w, h.w, l.w);
     qh[lane + 32 * i] = h;
     ql[lane + 32 * i] = l;
-  }
-}
-
-// softmax(q k^T) v over 1214 tokens, 12 heads x 64.  One query row per thread (q pre-scaled by
-// 64^-0.5 in the qkv epilogue -- a power of two, so identical to timm's post-scaling); keys/values of
-// the head stream through shared memory in tiles of 64 rows; online softmax.
-__global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv, float* __restrict__ oh,
-                                                        float* __restrict__ ol) {
-  constexpr int KT = 64;   // key/value rows per shared-memory tile (2 x 16 KB)
-  __shared__ __align__(16) float Ks[KT * HD];
-  __shared__ __align__(16) float Vs[KT * HD];
-  const int tid = threadIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const float* base = qkv + static_cast<size_t>(b) * TOK * (3 * D);
-  const int qi = blockIdx.x * 128 + tid;
-  const bool valid = qi < TOK;
-  float q[HD], acc[HD];
-  {
-    const float4* src = reinterpret_cast<const float4*>(base + static_cast<size_t>(valid ? qi : 0) * (3 * D) + h * HD);
-#pragma unroll
-    for (int c = 0; c < HD / 4; ++c) {
-      const float4 t = src[c];
-      q[c * 4 + 0] = t.x;
-      q[c * 4 + 1] = t.y;
-      q[c * 4 + 2] = t.z;
-      q[c * 4 + 3] = t.w;
-    }
-  }
-#pragma unroll
-  for (int d = 0; d < HD; ++d) acc[d] = 0.f;
-  float m = -INFINITY, l = 0.f;
-  for (int k0 = 0; k0 < TOK; k0 += KT) {
-    const int nk = min(KT, TOK - k0);
-    __syncthreads();
-    for (int idx = tid; idx < nk * (HD / 4); idx += 128) {
-      const int r = idx / (HD / 4), c4 = (idx % (HD / 4)) * 4;
-      const float* src = base + static_cast<size_t>(k0 + r) * (3 * D) + h * HD + c4;
-      *reinterpret_cast<float4*>(Ks + r * HD + c4) = *reinterpret_cast<const float4*>(src + D);
-      *reinterpret_cast<float4*>(Vs + r * HD + c4) = *reinterpret_cast<const float4*>(src + 2 * D);
-    }
-    __syncthreads();
-    for (int j0 = 0; j0 < nk; j0 += 4) {
-      float sc[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float* kr = Ks + min(j0 + u, nk - 1) * HD;
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-        for (int c = 0; c < HD / 4; ++c) {
-          const float4 t = *reinterpret_cast<const float4*>(kr + c * 4);
-          s0 = fmaf(q[c * 4 + 0], t.x, s0);
-          s1 = fmaf(q[c * 4 + 1], t.y, s1);
-          s0 = fmaf(q[c * 4 + 2], t.z, s0);
-          s1 = fmaf(q[c * 4 + 3], t.w, s1);
-        }
-        sc[u] = (j0 + u < nk) ? (s0 + s1) : -INFINITY;
-      }
-      const float cm = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
-      if (cm > m) {
-        const float f = expf(m - cm);
-        l *= f;
-#pragma unroll
-        for (int d = 0; d < HD; ++d) acc[d] *= f;
-        m = cm;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float pexp = expf(sc[u] - m);
-        l += pexp;
-        const float* vr = Vs + min(j0 + u, nk - 1) * HD;
-#pragma unroll
-        for (int c = 0; c < HD / 4; ++c) {
-          const float4 t = *reinterpret_cast<const float4*>(vr + c * 4);
-          acc[c * 4 + 0] = fmaf(pexp, t.x, acc[c * 4 + 0]);
-          acc[c * 4 + 1] = fmaf(pexp, t.y, acc[c * 4 + 1]);
-          acc[c * 4 + 2] = fmaf(pexp, t.z, acc[c * 4 + 2]);
-          acc[c * 4 + 3] = fmaf(pexp, t.w, acc[c * 4 + 3]);
-        }
-      }
-    }
-  }
-  if (valid) {
-    const float inv = 1.0f / l;
-    const size_t off = (static_cast<size_t>(b) * TOK + qi) * D + h * HD;
-#pragma unroll
-    for (int c = 0; c < HD / 4; ++c) {
-      float4 hh, ll;
-      split2(acc[c * 4 + 0] * inv, hh.x, ll.x);
-      split2(acc[c * 4 + 1] * inv, hh.y, ll.y);
-      split2(acc[c * 4 + 2] * inv, hh.z, ll.z);
-      split2(acc[c * 4 + 3] * inv, hh.w, ll.w);
-      *reinterpret_cast<float4*>(oh + off + c * 4) = hh;
-      *reinterpret_cast<float4*>(ol + off + c * 4) = ll;
-    }
   }
 }
 
@@ -339,7 +248,7 @@ static void free_impl(Weights& w) {
   Impl* im = static_cast<Impl*>(w.impl);
   if (!im) return;
   for (float* p : im->owned) cudaFree(p);
-  Buf* bufs[] = {&im->P, &im->tmp, &im->X, &im->Hn, &im->QKV, &im->O, &im->Hid, &im->pooled};
+  Buf* bufs[] = {&im->P, &im->tmp, &im->X, &im->Hn, &im->Qp, &im->Kp, &im->Vp, &im->O, &im->Hid, &im->pooled};
   for (Buf* b : bufs) b->release();
   delete im;
   w.impl = nullptr;
@@ -434,7 +343,16 @@ int forward(Weights& w, int B, const float* fbank, float* con, float* emo, float
   CK(im->tmp.ensure(Mp * D));
   CK(im->X.ensure(2 * M * D));
   CK(im->Hn.ensure(2 * M * D));
-  CK(im->QKV.ensure(M * 3 * D));
+  {   // per-head q / k / v^T operand planes of the attention kernel; the pad rows / columns (tokens
+      // 1214..1279) are never written afterwards and must stay zero
+    const size_t pe = 2 * attn::plane_elems(cb);
+    Buf* qkv[3] = {&im->Qp, &im->Kp, &im->Vp};
+    for (Buf* b : qkv) {
+      if (b->n >= pe) continue;
+      CK(b->ensure(pe));
+      CK(cudaMemsetAsync(b->p, 0, pe * sizeof(float), st));
+    }
+  }
   CK(im->O.ensure(2 * M * D));
   CK(im->Hid.ensure(2 * M * FF));
   CK(im->pooled.ensure(static_cast<size_t>(cb) * D));
@@ -446,6 +364,7 @@ int forward(Weights& w, int B, const float* fbank, float* con, float* emo, float
     float *Ph = im->P.p, *Pl = im->P.p + Mp * 256;
     float *Xh = im->X.p, *Xl = im->X.p + M * D, *Hh = im->Hn.p, *Hl = im->Hn.p + M * D;
     float *Oh = im->O.p, *Ol = im->O.p + M * D, *Fh = im->Hid.p, *Fl = im->Hid.p + M * FF;
+    const size_t pe1 = attn::plane_elems(cb);
     im2col_kernel<<<mp, 256, 0, st>>>(fbank + static_cast<size_t>(b0) * 1024 * 128, Ph, Pl);
     CK(cudaGetLastError());
     ++n_launch;
@@ -466,11 +385,13 @@ int forward(Weights& w, int B, const float* fbank, float* con, float* emo, float
         g = tc::GemmDesc{};
         g.A_hi = Hh; g.A_lo = Hl; g.lda = D;
         g.W_hi = k.qkv_w; g.W_lo = k.qkv_w + static_cast<size_t>(3) * D * D; g.ldw = D;
-        g.M = m; g.N = 3 * D; g.K = D; g.bias = k.qkv_b; g.C = im->QKV.p; g.ldc = 3 * D;
-        g.q_cols = D; g.q_scale = 0.125f;
-        CK(tc::gemm(tc::EPI_QKV, g, st));
-        attention_kernel<<<dim3((TOK + 127) / 128, HEADS, nb), 128, 0, st>>>(im->QKV.p, Oh, Ol);
-        CK(cudaGetLastError());
+        g.M = m; g.N = 3 * D; g.K = D; g.bias = k.qkv_b;
+        g.q_scale = 0.125f * 1.4426950408889634f;   // head_dim^-0.5 (timm Attention.scale) * log2(e): ex2 softmax
+        g.q_hi = im->Qp.p; g.q_lo = im->Qp.p + pe1; g.k_hi = im->Kp.p; g.k_lo = im->Kp.p + pe1;
+        g.vt_hi = im->Vp.p; g.vt_lo = im->Vp.p + pe1; g.tok = TOK; g.tokp = attn::kTokP; g.heads = HEADS;
+        CK(tc::gemm(tc::EPI_QKV_HEADS, g, st));
+        attn::AttnArgs aa{g.q_hi, g.q_lo, g.k_hi, g.k_lo, g.vt_hi, g.vt_lo, Oh, Ol, nb};
+        CK(attn::attention(aa, st));
         g = tc::GemmDesc{};
         g.A_hi = Oh; g.A_lo = Ol; g.lda = D;
         g.W_hi = k.proj_w; g.W_lo = k.proj_w + static_cast<size_t>(D) * D; g.ldw = D;

@@ -288,7 +288,40 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
         }
         if (!row_ok) continue;
-        if (EPI == EPI_PLAIN || EPI == EPI_QKV) {
+        if (EPI == EPI_QKV_HEADS) {
+          const int D = d.heads * 64;
+          const int which = nc / D, rem = nc - which * D, hd = rem >> 6, d0 = rem & 63;   // warp-uniform
+          const int b = m / d.tok, t = m - b * d.tok;
+          const size_t bh = static_cast<size_t>(b) * d.heads + hd;
+          if (which == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= d.q_scale;
+          }
+          if (which < 2) {
+            const size_t off = (bh * d.tokp + t) * 64 + d0;
+            float4* oh = reinterpret_cast<float4*>((which == 0 ? d.q_hi : d.k_hi) + off);
+            float4* ol = reinterpret_cast<float4*>((which == 0 ? d.q_lo : d.k_lo) + off);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 h, l;
+              split_tf32(v[i * 4 + 0], h.x, l.x);
+              split_tf32(v[i * 4 + 1], h.y, l.y);
+              split_tf32(v[i * 4 + 2], h.z, l.z);
+              split_tf32(v[i * 4 + 3], h.w, l.w);
+              oh[i] = h;
+              ol[i] = l;
+            }
+          } else {   // v transposed: consecutive lanes = consecutive tokens -> coalesced 128-B stores
+            const size_t off = (bh * 64 + d0) * d.tokp + t;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float h, l;
+              split_tf32(v[i], h, l);
+              d.vt_hi[off + static_cast<size_t>(i) * d.tokp] = h;
+              d.vt_lo[off + static_cast<size_t>(i) * d.tokp] = l;
+            }
+          }
+        } else if (EPI == EPI_PLAIN || EPI == EPI_QKV) {
           float* dst = d.C + static_cast<size_t>(m) * d.ldc + nc;
           if (nc + 32 <= d.N && (d.ldc & 3) == 0) {
 #pragma unroll
@@ -341,11 +374,11 @@ cudaError_t load_encode() {
 }
 
 // row-major fp32 [rows][cols] with leading dimension ld (floats): box = 32 cols x 128 rows, 128-B swizzle
-cudaError_t make_map(CUtensorMap* tm, const float* ptr, int rows, int cols, int ld) {
+cudaError_t make_map(CUtensorMap* tm, const float* ptr, int rows, int cols, int ld, int box_rows = BM) {
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld & 3)) return cudaErrorInvalidValue;
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 4};
-  const cuuint32_t box[2] = {BK, BM};
+  const cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -380,6 +413,13 @@ __global__ void split_planes_kernel(const float* __restrict__ src, float* __rest
 
 }  // namespace
 
+cudaError_t make_map_2d(CUtensorMap* tm, const float* ptr, int rows, int cols, int ld, int box_rows) {
+  cudaError_t e = load_encode();
+  if (e != cudaSuccess) return e;
+  if (box_rows < 8 || box_rows > 256 || (box_rows & 7)) return cudaErrorInvalidValue;
+  return make_map(tm, ptr, rows, cols, ld, box_rows);
+}
+
 cudaError_t gemm(int epi, const GemmDesc& din, cudaStream_t st) {
   GemmDesc d = din;
   if (d.K % BK != 0 || d.M < 1 || d.N < 1) return cudaErrorInvalidValue;
@@ -387,6 +427,8 @@ cudaError_t gemm(int epi, const GemmDesc& din, cudaStream_t st) {
   if (d.k_split % BK != 0) return cudaErrorInvalidValue;
   if ((epi == EPI_RES_LN_PLANES || epi == EPI_RES_LN_CROSS_LN_PLANES) && d.N != 128) return cudaErrorInvalidValue;
   if (d.ln_eps == 0.f) d.ln_eps = kLnEps;
+  if (epi == EPI_QKV_HEADS && (d.N != 3 * d.heads * 64 || d.tok < 1 || d.tokp < d.tok || !d.q_hi || !d.vt_lo))
+    return cudaErrorInvalidValue;
   cudaError_t e = load_encode();
   if (e != cudaSuccess) return e;
   CUtensorMap tm[6];
@@ -409,6 +451,7 @@ cudaError_t gemm(int epi, const GemmDesc& din, cudaStream_t st) {
     case EPI_RES_LN_PLANES: return launch<EPI_RES_LN_PLANES>(tm, d, st);
     case EPI_RES_LN_CROSS_LN_PLANES: return launch<EPI_RES_LN_CROSS_LN_PLANES>(tm, d, st);
     case EPI_RES_PLANES: return launch<EPI_RES_PLANES>(tm, d, st);
+    case EPI_QKV_HEADS: return launch<EPI_QKV_HEADS>(tm, d, st);
     default: return cudaErrorInvalidValue;
   }
 }

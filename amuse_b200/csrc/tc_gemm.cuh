@@ -19,6 +19,8 @@ enum Epi {
   EPI_RES_LN_PLANES = 4,          // N == 128: split(LN(acc + bias + (R_hi + R_lo)))
   EPI_RES_LN_CROSS_LN_PLANES = 5, // N == 128: split(LN2(LN(acc + bias + R) + cvec[row / rows_per_clip]))
   EPI_RES_PLANES = 6,   // C_hi/C_lo = split(acc + bias + (R_hi + R_lo))   (pre-norm residual, AST)
+  EPI_QKV_HEADS = 7,    // AST qkv (N = 3*heads*64): per-head operand planes for ast_attn.cu --
+                        //   q (scaled by q_scale), k -> [clip][head][tokp][64];  v -> transposed [clip][head][64][tokp]
 };
 
 struct Planes {
@@ -49,10 +51,17 @@ struct GemmDesc {
   int q_cols;
   float q_scale;
   float ln_eps;
+  // EPI_QKV_HEADS: row m = clip * tok + token
+  float *q_hi, *q_lo, *k_hi, *k_lo, *vt_hi, *vt_lo;
+  int tok, tokp, heads;
 };
 
 // Builds the TMA tensor maps for `d` and launches.  Returns cudaSuccess or the failing status.
 cudaError_t gemm(int epi, const GemmDesc& d, cudaStream_t st);
+
+// TMA tensor map over a row-major fp32 [rows][cols] matrix (leading dimension ld floats): boxes of
+// 32 columns (one 128-B swizzle row) x box_rows rows, SWIZZLE_128B -- the UMMA K-major operand layout.
+cudaError_t make_map_2d(CUtensorMap* tm, const float* ptr, int rows, int cols, int ld, int box_rows);
 
 // elementwise helper: split an fp32 tensor into hi/lo planes on the device
 cudaError_t split_planes(const float* src, float* hi, float* lo, size_t n, cudaStream_t st);
