@@ -106,9 +106,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
-      const int qrow = bh * kTokP + qblk * 256;
+    // ===================== TMA producer (whole warp in uniform control flow, one elected lane issues) =====
+    const int qrow = bh * kTokP + qblk * 256;
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, kQBytes);
 #pragma unroll
       for (int t = 0; t < 2; ++t)
@@ -117,11 +117,13 @@ __global__ void __launch_bounds__(kThreads, 1)
           tma_load_2d(smem + ((t * 2 + 0) * 2 + kb) * kQTile, &tmQ_hi, q_full, kb * 32, qrow + t * 128);
           tma_load_2d(smem + ((t * 2 + 1) * 2 + kb) * kQTile, &tmQ_lo, q_full, kb * 32, qrow + t * 128);
         }
-      const int krow = bh * kTokP, vrow = bh * kHD;
-      for (int j = 0; j < kNT; ++j) {
-        const int s = j % kStages;
-        mbar_wait(&kv_empty[s], ((j / kStages) & 1) ^ 1);
-        uint8_t* st = smem + kQBytes + s * kStageBytes;
+    }
+    const int krow = bh * kTokP, vrow = bh * kHD;
+    for (int j = 0; j < kNT; ++j) {
+      const int s = j % kStages;
+      mbar_wait(&kv_empty[s], ((j / kStages) & 1) ^ 1);
+      uint8_t* st = smem + kQBytes + s * kStageBytes;
+      if (elect_one()) {
         mbar_arrive_expect_tx(&kv_full[s], kStageBytes);
         tma_load_2d(st + 0 * kKBox, &tmK_hi, &kv_full[s], 0, krow + j * kKT);
         tma_load_2d(st + 1 * kKBox, &tmK_hi, &kv_full[s], 32, krow + j * kKT);
@@ -130,17 +132,18 @@ __global__ void __launch_bounds__(kThreads, 1)
         tma_load_2d(st + 4 * kKBox, &tmV_hi, &kv_full[s], j * kKT, vrow);
         tma_load_2d(st + 4 * kKBox + kVBox, &tmV_lo, &kv_full[s], j * kKT, vrow);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      // descriptors differ only in the 14-bit start-address field (bytes >> 4); every operand offset is
-      // a compile-time constant from the 1024-B aligned base, so they are formed by one 64-bit add
-      const uint64_t d0 = umma_desc(smem_u32(smem));
-      auto issue_S = [&](int t, int s) {
-        const uint64_t q0 = d0 + ((t * 4 * kQTile) >> 4);
-        const uint64_t k0 = d0 + ((kQBytes + s * kStageBytes) >> 4);
-        const uint32_t dS = tmem_base + kColS + t * kKT;
+    // ===================== MMA issuer (whole warp in uniform control flow, one elected lane issues) =====
+    // descriptors differ only in the 14-bit start-address field (bytes >> 4); every operand offset is
+    // a compile-time constant from the 1024-B aligned base, so they are formed by one 64-bit add
+    const uint64_t d0 = umma_desc(smem_u32(smem));
+    auto issue_S = [&](int t, int s) {
+      const uint64_t q0 = d0 + ((t * 4 * kQTile) >> 4);
+      const uint64_t k0 = d0 + ((kQBytes + s * kStageBytes) >> 4);
+      const uint32_t dS = tmem_base + kColS + t * kKT;
+      if (elect_one()) {
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
@@ -154,11 +157,14 @@ __global__ void __launch_bounds__(kThreads, 1)
             umma_tf32_ss(dS, a_hi, b_lo, kIdescS, 1u);
           }
         umma_commit(&s_full[t]);
-      };
-      auto issue_PV = [&](int t, int s, bool first) {
-        const uint64_t v0 = d0 + ((kQBytes + s * kStageBytes + 4 * kKBox) >> 4);
-        const uint32_t dO = tmem_base + kColO + t * kHD;
-        const uint32_t aP = tmem_base + kColP + t * 2 * kKT;
+      }
+      __syncwarp();
+    };
+    auto issue_PV = [&](int t, int s, bool first) {
+      const uint64_t v0 = d0 + ((kQBytes + s * kStageBytes + 4 * kKBox) >> 4);
+      const uint32_t dO = tmem_base + kColO + t * kHD;
+      const uint32_t aP = tmem_base + kColP + t * 2 * kKT;
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint64_t b_hi = v0 + ((k * 32) >> 4);
@@ -168,32 +174,34 @@ __global__ void __launch_bounds__(kThreads, 1)
           umma_tf32_ts(dO, aP + k * 8, b_lo, kIdescPV, 1u);
         }
         umma_commit(&pv_done[t]);
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      issue_S(0, 0);
-      issue_S(1, 0);
-      for (int j = 0; j < kNT; ++j) {
-        const int s = j % kStages;
-        if (j + 1 < kNT) {
-          const int s1 = (j + 1) % kStages;
-          mbar_wait(&kv_full[s1], ((j + 1) / kStages) & 1);
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            mbar_wait(&s_free[t], j & 1);
-            tc_fence_after();
-            issue_S(t, s1);
-          }
-        }
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    issue_S(0, 0);
+    issue_S(1, 0);
+    for (int j = 0; j < kNT; ++j) {
+      const int s = j % kStages;
+      if (j + 1 < kNT) {
+        const int s1 = (j + 1) % kStages;
+        mbar_wait(&kv_full[s1], ((j + 1) / kStages) & 1);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-          mbar_wait(&p_ready[t], j & 1);
+          mbar_wait(&s_free[t], j & 1);
           tc_fence_after();
-          issue_PV(t, s, j == 0);
+          issue_S(t, s1);
         }
-        umma_commit(&kv_empty[s]);   // stage s is free once S(j) and PV(j) of both tiles have read it
       }
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(&p_ready[t], j & 1);
+        tc_fence_after();
+        issue_PV(t, s, j == 0);
+      }
+      if (elect_one()) umma_commit(&kv_empty[s]);   // stage s is free once S(j), PV(j) of both tiles have read it
+      __syncwarp();
     }
   } else {
     // ===================== softmax / correction / epilogue =====================

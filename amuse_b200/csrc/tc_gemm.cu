@@ -21,6 +21,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace amuse {
 namespace tc {
@@ -164,14 +165,16 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
-        uint8_t* st = smem + s * STAGE_BYTES;
+    // ===================== TMA producer =====================
+    // (whole warp in uniform control flow, one elected lane issues: under `if (lane == 0)` the compiler wraps
+    //  every UTMALDG / UTCHMMA in an ELECT waterfall loop, ~50 issue cycles per instruction)
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
+      uint8_t* st = smem + s * STAGE_BYTES;
+      const int k0 = kb * BK;
+      if (tcp::elect_one()) {
         mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-        const int k0 = kb * BK;
         if (k0 < d.k_split) {
           tma_load_2d(st, &tmA_hi, &full[s], k0, m0);
           tma_load_2d(st + TILE_BYTES, &tmA_lo, &full[s], k0, m0);
@@ -182,28 +185,31 @@ __global__ void __launch_bounds__(kThreads, 1)
         tma_load_2d(st + 2 * TILE_BYTES, &tmW_hi, &full[s], k0, n0);
         tma_load_2d(st + 3 * TILE_BYTES, &tmW_lo, &full[s], k0, n0);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(&full[s], (kb / STAGES) & 1);
-        tc_fence_after();
-        const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+    // ===================== MMA issuer =====================
+    const uint64_t d0 = umma_desc(smem_u32(smem));
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      mbar_wait(&full[s], (kb / STAGES) & 1);
+      tc_fence_after();
+      if (tcp::elect_one()) {
+        const uint64_t base = d0 + ((s * STAGE_BYTES) >> 4);
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {   // UMMA_K = 8 for TF32: advance 32 B inside the 128-B swizzle row
-          const uint64_t a_hi = umma_desc(base + k * 32);
-          const uint64_t a_lo = umma_desc(base + TILE_BYTES + k * 32);
-          const uint64_t w_hi = umma_desc(base + 2 * TILE_BYTES + k * 32);
-          const uint64_t w_lo = umma_desc(base + 3 * TILE_BYTES + k * 32);
+          const uint64_t a_hi = base + ((k * 32) >> 4);
+          const uint64_t a_lo = base + ((TILE_BYTES + k * 32) >> 4);
+          const uint64_t w_hi = base + ((2 * TILE_BYTES + k * 32) >> 4);
+          const uint64_t w_lo = base + ((3 * TILE_BYTES + k * 32) >> 4);
           umma_tf32(tmem_base, a_hi, w_hi, (kb | k) ? 1u : 0u);
           umma_tf32(tmem_base, a_lo, w_hi, 1u);
           umma_tf32(tmem_base, a_hi, w_lo, 1u);
         }
         umma_commit(&empty[s]);            // frees the stage once the MMAs above have read it
+        if (kb == nkb - 1) umma_commit(acc_ready);   // accumulator complete
       }
-      umma_commit(acc_ready);              // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================

@@ -21,6 +21,19 @@ __device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* tm, u
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
+// One lane of a fully converged warp.  Code that issues tcgen05.mma / TMA must sit under warp-uniform
+// control flow with this predicate (not under `if (lane == 0)`): the operands of those instructions are
+// uniform registers, and in a divergent region the compiler wraps every one of them in an
+// ELECT / BRA.U.ANY "waterfall" loop (~50 issue cycles per MMA -- measured in the attention kernel).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -1,5 +1,5 @@
-"""AST (K5) timing + full-depth parity probe.  python scripts/ast_bench.py [B]"""
-import sys, time
+"""AST (K5) timing + full-depth parity probe.  python scripts/ast_bench.py [B]   (AST_DEPTH=n for a shallower stack)"""
+import os, sys, time
 from pathlib import Path
 import torch
 ROOT = Path(__file__).resolve().parents[1]
@@ -8,7 +8,8 @@ from amuse_b200.engine import Engine          # noqa: E402
 from oracle import weights as W, ast_ref as A  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-sd = W.ast_state_dict(depth=12)
+DEPTH = int(os.environ.get("AST_DEPTH", "12"))
+sd = W.ast_state_dict(depth=DEPTH)
 eng = Engine("cuda:0")
 eng.load_state_dict("ast", sd)
 eng.finalize()
@@ -20,7 +21,7 @@ torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record(); out = eng.ast_features(fbd); b.record(); torch.cuda.synchronize()
 ms = a.elapsed_time(b)
-print(f"AST 3 branches depth 12, B={B}: {ms:.1f} ms  -> {B * 783.08 / ms:.1f} TFLOP/s algorithmic, {B * 300 / ms * 1000:.0f} frames/s")
+print(f"AST 3 branches depth {DEPTH}, B={B}: {ms:.1f} ms  -> {B * 783.08 * DEPTH / 12 / ms:.1f} TFLOP/s algorithmic, {B * 300 / ms * 1000:.0f} frames/s")
 if "--parity" in sys.argv:
     torch.set_num_threads(16)
     t0 = time.time()
