@@ -1058,9 +1058,12 @@ int amuse_debug_tc_gemm(amuse_ctx* ctx, int epi, int M, int N, int K, const floa
   if (!ctx || !A || !W || !bias || !C) return fail(ctx, AMUSE_E_INVALID, "bad argument");
   cudaSetDevice(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool pair = (epi & 0x100) != 0;   // route to the CTA-pair kernel (tc_gemm2.cu); residual is [M][N] there
+  epi &= 0xff;
   const int K1 = A2 ? k_split : K, K2 = K - K1;
+  const int ldr = pair ? N : 128;
   const size_t nA = static_cast<size_t>(M) * K1, nA2 = static_cast<size_t>(M) * K2, nW = static_cast<size_t>(N) * K;
-  const size_t nC = static_cast<size_t>(M) * N, nR = R ? static_cast<size_t>(M) * 128 : 0;
+  const size_t nC = static_cast<size_t>(M) * N, nR = R ? static_cast<size_t>(M) * ldr : 0;
   DevBuf buf;
   CU(buf.ensure(2 * (nA + nA2 + nW + nC + nR)));
   float* p = buf.p;
@@ -1077,11 +1080,11 @@ int amuse_debug_tc_gemm(amuse_ctx* ctx, int epi, int M, int N, int K, const floa
   d.W_hi = w_hi; d.W_lo = w_lo; d.ldw = K;
   d.M = M; d.N = N; d.K = K; d.bias = bias;
   d.C = C; d.C_hi = c_hi; d.C_lo = c_lo; d.ldc = N;
-  d.R_hi = r_hi; d.R_lo = r_lo; d.ldr = 128;
+  d.R_hi = r_hi; d.R_lo = r_lo; d.ldr = ldr;
   if (ln) { d.ln_g = ln; d.ln_b = ln + 128; d.ln2_g = ln + 256; d.ln2_b = ln + 384; }
   d.cvec = cvec; d.rows_per_clip = rows_per_clip > 0 ? rows_per_clip : 1;
   d.q_cols = 128; d.q_scale = 0.17677669529663687f;
-  CU(tc::gemm(epi, d, st));
+  CU(pair ? tc::gemm2(epi, d, st) : tc::gemm(epi, d, st));
   ctx->launches++;
   if (epi != tc::EPI_PLAIN && epi != tc::EPI_QKV) {   // recombine the planes for the caller
     CU(launch_add_planes(c_hi, c_lo, C, nC, st));

@@ -24,7 +24,9 @@ namespace ast {
 namespace {
 
 constexpr int D = 768, HEADS = 12, HD = 64, TOK = 1214, PATCH = 1212, FF = 3072, FEAT = 256;
-constexpr int kChunk = 16;   // clips per pass
+// clips per pass: 15 clips = 72 row tiles of 256, so the N = 768 GEMMs have 216 pair tiles = 2.92 waves of
+// the 74 CTA pairs (16 clips would be 228 tiles = 3.08 waves, i.e. a fourth, almost empty wave)
+constexpr int kChunk = 15;
 
 struct Buf {
   float* p = nullptr;
@@ -374,7 +376,7 @@ int forward(Weights& w, int B, const float* fbank, float* con, float* emo, float
       g.A_hi = Ph; g.A_lo = Pl; g.lda = 256;
       g.W_hi = br.patch_w; g.W_lo = br.patch_w + static_cast<size_t>(D) * 256; g.ldw = 256;
       g.M = mp; g.N = D; g.K = 256; g.bias = br.patch_b; g.C = im->tmp.p; g.ldc = D;
-      CK(tc::gemm(tc::EPI_PLAIN, g, st));
+      CK(tc::gemm2(tc::EPI_PLAIN, g, st));
       assemble_kernel<<<m, 192, 0, st>>>(im->tmp.p, br.cls, br.dist, br.pos, Xh, Xl);
       CK(cudaGetLastError());
       n_launch += 2;
@@ -389,7 +391,7 @@ int forward(Weights& w, int B, const float* fbank, float* con, float* emo, float
         g.q_scale = 0.125f * 1.4426950408889634f;   // head_dim^-0.5 (timm Attention.scale) * log2(e): ex2 softmax
         g.q_hi = im->Qp.p; g.q_lo = im->Qp.p + pe1; g.k_hi = im->Kp.p; g.k_lo = im->Kp.p + pe1;
         g.vt_hi = im->Vp.p; g.vt_lo = im->Vp.p + pe1; g.tok = TOK; g.tokp = attn::kTokP; g.heads = HEADS;
-        CK(tc::gemm(tc::EPI_QKV_HEADS, g, st));
+        CK(tc::gemm2(tc::EPI_QKV_HEADS, g, st));
         attn::AttnArgs aa{g.q_hi, g.q_lo, g.k_hi, g.k_lo, g.vt_hi, g.vt_lo, Oh, Ol, nb};
         CK(attn::attention(aa, st));
         g = tc::GemmDesc{};
@@ -397,20 +399,20 @@ int forward(Weights& w, int B, const float* fbank, float* con, float* emo, float
         g.W_hi = k.proj_w; g.W_lo = k.proj_w + static_cast<size_t>(D) * D; g.ldw = D;
         g.M = m; g.N = D; g.K = D; g.bias = k.proj_b;
         g.R_hi = Xh; g.R_lo = Xl; g.ldr = D; g.C_hi = Xh; g.C_lo = Xl; g.ldc = D;   // x += proj(o), in place
-        CK(tc::gemm(tc::EPI_RES_PLANES, g, st));
+        CK(tc::gemm2(tc::EPI_RES_PLANES, g, st));
         ln_rows_kernel<<<(m + 7) / 8, 256, 0, st>>>(Xh, Xl, k.ln2, k.ln2b, 1e-6f, Hh, Hl, m);
         CK(cudaGetLastError());
         g = tc::GemmDesc{};
         g.A_hi = Hh; g.A_lo = Hl; g.lda = D;
         g.W_hi = k.fc1_w; g.W_lo = k.fc1_w + static_cast<size_t>(FF) * D; g.ldw = D;
         g.M = m; g.N = FF; g.K = D; g.bias = k.fc1_b; g.C_hi = Fh; g.C_lo = Fl; g.ldc = FF;
-        CK(tc::gemm(tc::EPI_GELU_PLANES, g, st));
+        CK(tc::gemm2(tc::EPI_GELU_PLANES, g, st));
         g = tc::GemmDesc{};
         g.A_hi = Fh; g.A_lo = Fl; g.lda = FF;
         g.W_hi = k.fc2_w; g.W_lo = k.fc2_w + static_cast<size_t>(D) * FF; g.ldw = FF;
         g.M = m; g.N = D; g.K = FF; g.bias = k.fc2_b;
         g.R_hi = Xh; g.R_lo = Xl; g.ldr = D; g.C_hi = Xh; g.C_lo = Xl; g.ldc = D;   // x += fc2(h), in place
-        CK(tc::gemm(tc::EPI_RES_PLANES, g, st));
+        CK(tc::gemm2(tc::EPI_RES_PLANES, g, st));
         n_launch += 7;
       }
       ln_rows_kernel<<<(m + 7) / 8, 256, 0, st>>>(Xh, Xl, br.norm_w, br.norm_b, 1e-6f, Hh, Hl, m);

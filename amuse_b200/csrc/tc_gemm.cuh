@@ -59,6 +59,11 @@ struct GemmDesc {
 // Builds the TMA tensor maps for `d` and launches.  Returns cudaSuccess or the failing status.
 cudaError_t gemm(int epi, const GemmDesc& d, cudaStream_t st);
 
+// The same contract on the CTA-pair kernel (tc_gemm2.cu: 256x256 tiles on two SMs, persistent, epilogue
+// overlapped with the next tile): N % 256 == 0, single A source, EPI_PLAIN / EPI_GELU_PLANES /
+// EPI_RES_PLANES / EPI_QKV_HEADS.  Used for the AST GEMMs.
+cudaError_t gemm2(int epi, const GemmDesc& d, cudaStream_t st);
+
 // TMA tensor map over a row-major fp32 [rows][cols] matrix (leading dimension ld floats): boxes of
 // 32 columns (one 128-B swizzle row) x box_rows rows, SWIZZLE_128B -- the UMMA K-major operand layout.
 cudaError_t make_map_2d(CUtensorMap* tm, const float* ptr, int rows, int cols, int ld, int box_rows);

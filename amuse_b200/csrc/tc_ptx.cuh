@@ -92,6 +92,50 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t base) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(COLS) : "memory");
 }
 
+// ---- CTA-pair (cta_group::2) variants: two CTAs of a cluster on one TPC act as one MMA unit ------------
+// D[256 x N]: rows [0,128) accumulate in the leader's TMEM, rows [128,256) in the peer's; A = each CTA's
+// own 128 rows, B = N/2 rows from each CTA (same shared-memory offsets in both).  Issued by the leader only.
+__device__ __forceinline__ void umma2_tf32_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once the MMAs issued so far have completed) on the barrier at this shared-memory offset in
+// every CTA of `cta_mask`
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+// TMA load into THIS CTA's shared memory; the bytes are credited to the barrier at `bar_cluster_addr`
+// (a shared::cluster address -- the pair leader's "full" barrier)
+__device__ __forceinline__ void tma2_load_2d(void* smem, const CUtensorMap* tm, uint32_t bar_cluster_addr, int c0,
+                                             int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(smem)),
+      "l"(tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem2_alloc(uint32_t* slot) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem2_dealloc(uint32_t base) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(COLS) : "memory");
+}
+
 // 32 lanes x 32 columns: thread `lane` of the warp gets columns [col, col+32) of its TMEM lane.
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];

@@ -63,3 +63,26 @@ def test_epilogues(engine):
     ref = A.double() @ W3.double().T + b3.double()
     ref[:, :128] *= 0.17677669529663687
     assert (engine.debug_tc_gemm(EPI_QKV, A, W3, b3).cpu().double() - ref).abs().max().item() < 2e-5
+
+
+PAIR = 0x100   # route debug_tc_gemm to the CTA-pair kernel (csrc/tc_gemm2.cu)
+
+
+@pytest.mark.parametrize("M,N,K", [(2424, 768, 256), (1214, 2304, 768), (300, 768, 3072), (19424, 256, 96)])
+def test_pair_kernel_plain(engine, M, N, K):
+    """cta_group::2 persistent GEMM: ragged M tails, several tiles per pair (double-buffered accumulators)."""
+    A, W, b = _rand(M, K, seed=1), _rand(N, K, seed=2, scale=1 / math.sqrt(K)), _rand(N, seed=3)
+    got = engine.debug_tc_gemm(EPI_PLAIN | PAIR, A, W, b).cpu().double()
+    ref = A.double() @ W.double().T + b.double()
+    err = (got - ref).abs().max().item()
+    print(f"[tc_gemm2] {M}x{N}x{K}: 3xTF32 max|err|={err:.2e}")
+    assert err < 4e-8 * K * max(1.0, ref.abs().max().item() / 4) + 1e-5
+
+
+def test_pair_kernel_epilogues(engine):
+    M, N, K = 40000, 768, 128      # 157 row tiles x 3: more tiles than CTA pairs -> persistent loop + both buffers
+    A, W, b = _rand(M, K, seed=1), _rand(N, K, seed=2, scale=1 / math.sqrt(K)), _rand(N, seed=3)
+    R = _rand(M, N, seed=5)
+    y = A.double() @ W.double().T + b.double()
+    assert (engine.debug_tc_gemm(EPI_GELU | PAIR, A, W, b).cpu().double() - F.gelu(y)).abs().max().item() < 2e-5
+    assert (engine.debug_tc_gemm(EPI_RES | PAIR, A, W, b, R=R).cpu().double() - (y + R.double())).abs().max().item() < 2e-5
