@@ -3,11 +3,15 @@
 // One CTA = one (clip, head, block of 256 queries) = two 128-row query tiles that share every
 // key/value tile (halves the L2 -> SM traffic per MMA; with one tile per CTA the K/V stream alone
 // would need ~42 B/clk/SM, the whole L2 fabric).  Key/value tiles are 32 keys wide.
-//   warp 0      TMA producer: Q_hi/Q_lo of both query tiles once (128 KB), then per key tile
-//               K_hi, K_lo (32 x 64) and V^T_hi, V^T_lo (64 x 32) into a 3-stage ring (32 KB / stage)
-//   warp 1      TMEM allocation + MMA issue (one lane):
-//                 S_t  = Q_t . K^T        A, B from shared memory   3 x 8 tcgen05.mma  M128 N32 K8
+//   warp 0      TMA producer: Q_lo of both query tiles once (64 KB), then per key tile
+//               K_hi, K_lo (32 x 64) and V^T_hi, V^T_lo (64 x 32) into a 5-stage ring (32 KB / stage)
+//   warp 1      TMEM allocation + MMA issue (one elected lane):
+//                 S_t  = Q_t . K^T        3 x 8 tcgen05.mma  M128 N32 K8;  Q_hi is the A operand FROM TMEM
+//                                         (Q_hi.K_hi, Q_hi.K_lo), only Q_lo.K_hi reads A from shared memory
 //                 O_t += P_t . V          A = P_t from TMEM          3 x 4 tcgen05.mma  M128 N64 K8
+//               An MMA whose A operand comes from shared memory costs ~60 cycles here whatever N is (the
+//               4 KB A slice is read at ~64 B/clk; ncu source view of the first version, where all 24
+//               score MMAs were of that kind) against 16 for the TMEM form.
 //               software-pipelined  S_0(j+1) S_1(j+1) PV_0(j) PV_1(j)  so the softmax of tile j
 //               overlaps the score MMAs of tile j+1
 //   warps 2-5   softmax of query tile 0, warps 6-9 of query tile 1: one query row per thread
@@ -31,9 +35,9 @@ using namespace tcp;
 constexpr int kThreads = 320;
 constexpr int kKT = 32;                         // keys per tile
 constexpr int kNT = (kTok + kKT - 1) / kKT;     // 38 key tiles
-constexpr int kStages = 3;
+constexpr int kStages = 5;
 constexpr int kQTile = 128 * 32 * 4;            // one 128-row x 32-column box: 16 KB
-constexpr int kQBytes = 8 * kQTile;             // 2 tiles x {hi, lo} x 2 column halves
+constexpr int kQBytes = 4 * kQTile;             // Q_lo: 2 tiles x 2 column halves
 constexpr int kKBox = kKT * 32 * 4;             // 32 keys x 32 columns: 4 KB
 constexpr int kVBox = kHD * kKT * 4;            // 64 d x 32 keys: 8 KB
 constexpr int kStageBytes = 4 * kKBox + 2 * kVBox;   // 32 KB
@@ -45,6 +49,7 @@ static_assert(kSmemBytes <= 232448, "exceeds the 227 KB shared-memory limit of s
 constexpr uint32_t kColO = 0;      // O_t : [t*64, t*64+64)
 constexpr uint32_t kColS = 128;    // S_t : [128 + t*32, +32)
 constexpr uint32_t kColP = 192;    // P_t : hi [192 + t*64, +32), lo [+32, +64)
+constexpr uint32_t kColQ = 320;    // Q_hi of tile t : [320 + t*64, +64)   (A operand of the score MMAs)
 constexpr int kTmemCols = 512;
 
 constexpr uint32_t kIdescS = idesc_tf32(128, kKT);
@@ -62,31 +67,33 @@ __global__ void __launch_bounds__(kThreads, 1)
     ast_attention_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ CUtensorMap tmQ_lo,
                          const __grid_constant__ CUtensorMap tmK_hi, const __grid_constant__ CUtensorMap tmK_lo,
                          const __grid_constant__ CUtensorMap tmV_hi, const __grid_constant__ CUtensorMap tmV_lo,
-                         float* __restrict__ o_hi, float* __restrict__ o_lo) {
+                         const float* __restrict__ q_hi, float* __restrict__ o_hi, float* __restrict__ o_lo) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);
-  uint64_t* q_full = bars;              // [1]
-  uint64_t* kv_full = bars + 1;         // [3]
-  uint64_t* kv_empty = bars + 4;        // [3]
-  uint64_t* s_full = bars + 7;          // [2]  MMA -> softmax t: S_t(j) complete
-  uint64_t* s_free = bars + 9;          // [2]  softmax t -> MMA: S_t(j) is in registers
-  uint64_t* p_ready = bars + 11;        // [2]  softmax t -> MMA: P_t(j) stored (and O_t rescaled)
-  uint64_t* pv_done = bars + 13;        // [2]  MMA -> softmax t: O_t += P_t(j) V(j) complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* q_full = bars;                   // [1]
+  uint64_t* qh_ready = bars + 1;             // [1]  softmax warps -> MMA: Q_hi of both tiles stored in TMEM
+  uint64_t* s_full = bars + 2;               // [2]  MMA -> softmax t: S_t(j) complete
+  uint64_t* s_free = bars + 4;               // [2]  softmax t -> MMA: S_t(j) is in registers
+  uint64_t* p_ready = bars + 6;              // [2]  softmax t -> MMA: P_t(j) stored (and O_t rescaled)
+  uint64_t* pv_done = bars + 8;              // [2]  MMA -> softmax t: O_t += P_t(j) V(j) complete
+  uint64_t* kv_full = bars + 10;             // [kStages]
+  uint64_t* kv_empty = kv_full + kStages;    // [kStages]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_empty + kStages);
+  static_assert((10 + 2 * kStages) * 8 + 4 <= 256, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qblk = blockIdx.x, head = blockIdx.y, clip = blockIdx.z;
   const int bh = clip * kHeads + head;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmQ_hi);
     prefetch_tmap(&tmQ_lo);
     prefetch_tmap(&tmK_hi);
     prefetch_tmap(&tmK_lo);
     prefetch_tmap(&tmV_hi);
     prefetch_tmap(&tmV_lo);
     mbar_init(q_full, 1);
+    mbar_init(qh_ready, 8);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
@@ -113,10 +120,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
       for (int t = 0; t < 2; ++t)
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          tma_load_2d(smem + ((t * 2 + 0) * 2 + kb) * kQTile, &tmQ_hi, q_full, kb * 32, qrow + t * 128);
-          tma_load_2d(smem + ((t * 2 + 1) * 2 + kb) * kQTile, &tmQ_lo, q_full, kb * 32, qrow + t * 128);
-        }
+        for (int kb = 0; kb < 2; ++kb)
+          tma_load_2d(smem + (t * 2 + kb) * kQTile, &tmQ_lo, q_full, kb * 32, qrow + t * 128);
     }
     const int krow = bh * kTokP, vrow = bh * kHD;
     for (int j = 0; j < kNT; ++j) {
@@ -140,21 +145,21 @@ __global__ void __launch_bounds__(kThreads, 1)
     // a compile-time constant from the 1024-B aligned base, so they are formed by one 64-bit add
     const uint64_t d0 = umma_desc(smem_u32(smem));
     auto issue_S = [&](int t, int s) {
-      const uint64_t q0 = d0 + ((t * 4 * kQTile) >> 4);
+      const uint64_t q0 = d0 + ((t * 2 * kQTile) >> 4);
       const uint64_t k0 = d0 + ((kQBytes + s * kStageBytes) >> 4);
       const uint32_t dS = tmem_base + kColS + t * kKT;
+      const uint32_t aQ = tmem_base + kColQ + t * kHD;
       if (elect_one()) {
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t a_hi = q0 + ((kb * kQTile + k * 32) >> 4);
-            const uint64_t a_lo = q0 + (((2 + kb) * kQTile + k * 32) >> 4);
+            const uint64_t a_lo = q0 + ((kb * kQTile + k * 32) >> 4);
             const uint64_t b_hi = k0 + ((kb * kKBox + k * 32) >> 4);
             const uint64_t b_lo = k0 + (((2 + kb) * kKBox + k * 32) >> 4);
-            umma_tf32_ss(dS, a_hi, b_hi, kIdescS, (kb | k) ? 1u : 0u);
+            umma_tf32_ts(dS, aQ + kb * 32 + k * 8, b_hi, kIdescS, (kb | k) ? 1u : 0u);
+            umma_tf32_ts(dS, aQ + kb * 32 + k * 8, b_lo, kIdescS, 1u);
             umma_tf32_ss(dS, a_lo, b_hi, kIdescS, 1u);
-            umma_tf32_ss(dS, a_hi, b_lo, kIdescS, 1u);
           }
         umma_commit(&s_full[t]);
       }
@@ -178,6 +183,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       __syncwarp();
     };
     mbar_wait(q_full, 0);
+    mbar_wait(qh_ready, 0);
     mbar_wait(&kv_full[0], 0);
     tc_fence_after();
     issue_S(0, 0);
@@ -211,6 +217,27 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t aS = lane_base + kColS + t * kKT;
     const uint32_t aP = lane_base + kColP + t * 2 * kKT;
     const uint32_t aO = lane_base + kColO + t * kHD;
+    {   // Q_hi row of this thread -> TMEM (pad rows of the planes are zero)
+      const float4* src = reinterpret_cast<const float4*>(
+          q_hi + (static_cast<size_t>(bh) * kTokP + qblk * 256 + t * 128 + q * 32 + lane) * kHD);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 x = __ldg(src + c * 8 + i);
+          v[i * 4 + 0] = x.x;
+          v[i * 4 + 1] = x.y;
+          v[i * 4 + 2] = x.z;
+          v[i * 4 + 3] = x.w;
+        }
+        tmem_st32(lane_base + kColQ + t * kHD + c * 32, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(qh_ready);
+    }
     float m = 0.f, l = 0.f;
     for (int j = 0; j < kNT; ++j) {
       mbar_wait(&s_full[t], j & 1);
@@ -314,7 +341,8 @@ cudaError_t attention(const AttnArgs& a, cudaStream_t st) {
   if ((e = tc::make_map_2d(&tm[4], a.vt_hi, v_rows, kTokP, kTokP, kHD)) != cudaSuccess) return e;
   if ((e = tc::make_map_2d(&tm[5], a.vt_lo, v_rows, kTokP, kTokP, kHD)) != cudaSuccess) return e;
   dim3 grid(kTokP / 256, kHeads, a.nb);
-  ast_attention_kernel<<<grid, kThreads, kSmemBytes, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], a.o_hi, a.o_lo);
+  ast_attention_kernel<<<grid, kThreads, kSmemBytes, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], a.q_hi, a.o_hi,
+                                                           a.o_lo);
   return cudaGetLastError();
 }
 

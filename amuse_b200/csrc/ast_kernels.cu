@@ -24,9 +24,10 @@ namespace ast {
 namespace {
 
 constexpr int D = 768, HEADS = 12, HD = 64, TOK = 1214, PATCH = 1212, FF = 3072, FEAT = 256;
-// clips per pass: 15 clips = 72 row tiles of 256, so the N = 768 GEMMs have 216 pair tiles = 2.92 waves of
-// the 74 CTA pairs (16 clips would be 228 tiles = 3.08 waves, i.e. a fourth, almost empty wave)
-constexpr int kChunk = 15;
+// Clips per pass.  One pass costs whole waves: the GEMMs run ceil(tiles / 74 CTA pairs) rounds of 256x256
+// tiles and the attention ceil(60 * clips / 148) rounds of CTAs, so the batch is cut into equal passes of
+// at most 32 clips (32 clips: attention 12.97 waves, N = 768 GEMMs 6.16 waves; workspace ~2 GB)
+constexpr int kChunkMax = 32;
 
 struct Buf {
   float* p = nullptr;
@@ -339,7 +340,9 @@ int forward(Weights& w, int B, const float* fbank, float* con, float* emo, float
       return AMUSE_E_CUDA;                                   \
     }                                                        \
   } while (0)
-  const int cb = std::min(B, kChunk);
+  const int n_pass = (B + kChunkMax - 1) / kChunkMax;
+  const int kChunk = (B + n_pass - 1) / n_pass;
+  const int cb = kChunk;
   const size_t Mp = static_cast<size_t>(cb) * PATCH, M = static_cast<size_t>(cb) * TOK;
   CK(im->P.ensure(2 * Mp * 256));
   CK(im->tmp.ensure(Mp * D));
