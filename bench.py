@@ -37,6 +37,8 @@ N_STEPS = 1000
 SAMPLER = "ddpm"
 FLOP_DENOISE_PER_CLIP_STEP = 19.219e6      # BASELINE.md section 3 (2*M*N*K of every GEMM incl. QK^T, AV)
 FLOP_DECODE_PER_CLIP = 1.7595e9
+FLOP_AST_PER_CLIP = 783.08e9               # 3 branches x 261.03 GFLOP
+AUDIO_SAMPLES = 160000                     # 10 s at 16 kHz
 METRIC = "SMPL-X pose frames/sec over full DDPM sampling (10 s clip, batch 64)"
 
 
@@ -267,6 +269,77 @@ def run_ours(args, rank, world, local_rank):
     t_e2e = sum(e[0].elapsed_time(e[1]) for e in evh) / 1e3
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- scope E: synthetic 10 s / 16 kHz audio -> on-device Kaldi fbank -> 3 AST encoders ->
+    #      the same sampler + decode.  Reported beside the headline (scope S); AST weights: seeded random
+    #      init of the reference architecture (no checkpoints offline), broadcast from rank 0.
+    scope_e = None
+    if not args.no_audio:
+        ast = W.ast_state_dict(depth=12)
+        for k in ast:
+            t = ast[k].to(dev)
+            if world > 1:
+                dist.broadcast(t, src=0)
+            ast[k] = t
+        eng.load_state_dict("ast", ast)
+        del ast
+        eng.finalize()
+        wav_h = (0.1 * torch.randn(B, AUDIO_SAMPLES, generator=torch.Generator().manual_seed(7 + rank))).pin_memory()
+        wav_d = wav_h.to(dev)
+
+        def audio_step(ev=None, host=False):
+            if ev:
+                ev[0].record()
+            w = wav_h.to(dev, non_blocking=True) if host else wav_d
+            fb = eng.fbank(w)
+            if ev:
+                ev[1].record()
+            con, emo, sty = eng.ast_features(fb)
+            if ev:
+                ev[2].record()
+            z = eng.denoise(d[0], con, emo, sty, n_steps=N_STEPS, sampler=SAMPLER, seed=seed)
+            poses, trans = eng.decode(z)
+            if host:
+                out_poses.copy_(poses, non_blocking=True)
+                out_trans.copy_(trans, non_blocking=True)
+            if ev:
+                ev[3].record()
+
+        for _ in range(max(1, args.warmup - 1)):
+            audio_step()
+        ks = max(1, min(args.steps, 3))
+        eva = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(2 * ks)]
+        la = eng.launch_count()
+        barrier()
+        for i in range(ks):
+            flush.fill_(i & 0xFF)
+            audio_step(eva[i])
+        barrier()
+        launches_e = (eng.launch_count() - la) // ks
+        for i in range(ks):
+            flush.fill_(i & 0xFF)
+            audio_step(eva[ks + i], host=True)
+        barrier()
+        te = torch.tensor([sum(e[0].elapsed_time(e[3]) for e in eva[:ks]), sum(e[0].elapsed_time(e[1]) for e in eva[:ks]),
+                           sum(e[1].elapsed_time(e[2]) for e in eva[:ks]), sum(e[0].elapsed_time(e[3]) for e in eva[ks:])],
+                          dtype=torch.float64, device=dev) / ks
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        t_all, t_fb, t_ast, t_all_host = te.tolist()
+        peak_tf0 = load_peaks()[0]
+        scope_e = {"what": "10 s / 16 kHz synthetic audio -> Kaldi fbank (device) -> 3x AST (DeiT-base, 1214 tokens, tcgen05 3xTF32) "
+                           f"-> {SAMPLER}{N_STEPS} sampler -> decode; {B} clips/GPU",
+                   "value": world * B * FRAMES / (t_all / 1e3), "unit": "frames/s", "ms_per_step": t_all,
+                   "fbank_ms": t_fb, "ast_ms": t_ast, "sampler_decode_ms": t_all - t_fb - t_ast,
+                   "e2e_host_audio": {"value": world * B * FRAMES / (t_all_host / 1e3), "unit": "frames/s",
+                                      "h2d_bytes_per_step": wav_h.numel() * 4 + h[0].numel() * 4, "d2h_bytes_per_step":
+                                      out_poses.numel() * 4 + out_trans.numel() * 4},
+                   "gpu_launches": int(launches_e),
+                   "ast_roofline": {"bound": "tensor", "achieved": B * FLOP_AST_PER_CLIP / (t_ast / 1e3) / 1e12,
+                                    "peak": peak_tf0, "unit": "TFLOP/s",
+                                    "frac": B * FLOP_AST_PER_CLIP / (t_ast / 1e3) / 1e12 / peak_tf0,
+                                    "note": "algorithmic 783.08 GFLOP/clip; fp32-accurate 3xTF32 issues 3 TF32 MMAs per "
+                                            "product, i.e. 6x the bf16 tensor time, so frac <= 1/6 by construction"}}
+
     # one gather of the poses to rank 0 (north_star: gather at the end), timed separately
     gather_ms = None
     if world > 1:
@@ -298,23 +371,27 @@ def run_ours(args, rank, world, local_rank):
 
     # CPU baseline: bounded sample of the same workload on the host cores (oracle port)
     den_c, vae_c = W.denoiser_state_dict(), W.motionprior_state_dict()
-    pick_cpu_threads(den_c, B)
-    cpu_reference_step(den_c, vae_c, B, 5, SAMPLER)
     cs = 100
-    t_cpu, _ = cpu_reference_step(den_c, vae_c, B, cs, SAMPLER)
-    from oracle import lpdm_ref as R
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        R.feats_to_motion(R.vae_decode(vae_c, torch.randn(B, 128)))
-    t_cdec = time.perf_counter() - t0
-    t_cpu_full = (t_cpu - t_cdec) * (N_STEPS / cs) + t_cdec
-    cpu_value = B * FRAMES / t_cpu_full
+    cpu_value = None
+    if not args.no_baselines:
+        pick_cpu_threads(den_c, B)
+        cpu_reference_step(den_c, vae_c, B, 5, SAMPLER)
+        t_cpu, _ = cpu_reference_step(den_c, vae_c, B, cs, SAMPLER)
+        from oracle import lpdm_ref as R
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            R.feats_to_motion(R.vae_decode(vae_c, torch.randn(B, 128)))
+        t_cdec = time.perf_counter() - t0
+        t_cpu_full = (t_cpu - t_cdec) * (N_STEPS / cs) + t_cdec
+        cpu_value = B * FRAMES / t_cpu_full
 
     # PyTorch-eager on the SAME GPU (the reference's own execution model: one ATen launch per op), via
     # the oracle port moved to the device -- a reported baseline only (north_star: ">= 10x the
     # reference single-GPU infer_gesture wall-clock"); bounded sample, scaled like the CPU one.
     eager = None
     try:
+        if args.no_baselines:
+            raise RuntimeError("--no-baselines")
         den_g = {k: v.to(dev) for k, v in den_c.items()}
         vae_g = {k: v.to(dev) for k, v in vae_c.items()}
         gi = [t.to(dev) for t in synth_inputs(B)]
@@ -357,6 +434,7 @@ def run_ours(args, rank, world, local_rank):
                          "sample": f"B={B}: {cs} of {N_STEPS} denoiser steps timed and scaled x{N_STEPS // cs}, plus one full decode; "
                                    f"thread count auto-picked from a probe (host has {os.cpu_count()} logical CPUs)"},
         "eager_gpu_baseline": eager,
+        "scope_E": scope_e,
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
@@ -368,6 +446,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-baselines", action="store_true",
+                    help="skip the CPU-oracle and PyTorch-eager baselines (profiling runs under ncu)")
+    ap.add_argument("--no-audio", action="store_true", help="skip the scope-E (audio -> AST -> sampler) measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

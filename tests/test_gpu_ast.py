@@ -32,7 +32,7 @@ def test_ast_features_vs_oracle(depth, B):
         e64 = (got.cpu().double() - ref64).abs().max().item()
         r = (ref.double() - ref64).abs().max().item()
         print(f"[parity] ast depth={depth} {name}: |cuda-f64|={e64:.3e} |f32ref-f64|={r:.3e} |feat|max={ref64.abs().max():.2f}")
-        assert e64 < 2e-3
+        assert e64 < 3e-4      # measured 4-5e-5 (tensor-core RZ accumulation over K = 768..3072)
     eng.close()
 
 
@@ -48,7 +48,7 @@ def test_process_single_seq_shapes_and_fbank():
     fb = A.fbank_features(wav - wav.mean())
     assert fb.shape == (1024, 128) and abs(float(fb[1000:, :].mean()) - 0.906) < 1e-2     # padded rows after normalisation
     rc, re, rs = A.ast_features(ast, fb[None])
-    assert (con.cpu() - rc).abs().max().item() < 2e-3
+    assert (con.cpu() - rc).abs().max().item() < 3e-4
     out = m.diffusion_backward(1, con, emo, sty)
     assert out["poses"].shape == (1, 300, 55, 3) and torch.isfinite(out["poses"]).all()
     m.engine.close()
