@@ -15,6 +15,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "ast_attn.cuh"
 #include "ast_kernels.cuh"
 #include "common.cuh"
 #include "decode_kernels.cuh"
@@ -1109,6 +1110,15 @@ int amuse_fbank(amuse_ctx* ctx, int B, int n_samples, const float* wave, float n
   }
   CU(fb::launch(wave, B, n_samples, ctx->mel_t.p, norm_mean, norm_std, fbank, st));
   ctx->launches++;
+  return AMUSE_OK;
+}
+
+int amuse_debug_attn_profile(amuse_ctx* ctx, int enable, int64_t* stamps, int n) {
+  if (!ctx) return AMUSE_E_INVALID;
+  cudaSetDevice(ctx->device);
+  CU(cudaDeviceSynchronize());
+  static_assert(sizeof(long long) == sizeof(int64_t), "stamp type");
+  CU(attn::debug_profile(enable, reinterpret_cast<long long*>(stamps), n));
   return AMUSE_OK;
 }
 

@@ -57,6 +57,15 @@ constexpr int kTmemCols = 512;
 constexpr uint32_t kIdescS = idesc_tf32(128, kKT);
 constexpr uint32_t kIdescPV = idesc_tf32(128, kHD);
 
+}  // namespace
+// debug timeline (amuse_debug_attn_profile): clock64 stamps of CTA (0,0,0) for key tiles j in [8, 12)
+__device__ long long* g_prof = nullptr;
+namespace {
+#define ATTN_PROF(slot)                                                                      \
+  do {                                                                                       \
+    if (prof && j >= 8 && j < 12) prof[((j - 8) * 16 + (slot))] = clock64();                 \
+  } while (0)
+
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -85,6 +94,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qblk = blockIdx.x, head = blockIdx.y, clip = blockIdx.z;
   const int bh = clip * kHeads + head;
+  long long* const prof = (g_prof && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && lane == 0) ? g_prof : nullptr;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmK_hi);
@@ -177,15 +187,19 @@ __global__ void __launch_bounds__(kThreads, 1)
       const bool more = j + 1 < kNT;
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
+        ATTN_PROF(8 + t * 4 + 0);            // MMA warp: about to wait for P_t(j)
         mbar_wait(&p_ready[t], j & 1);
+        ATTN_PROF(8 + t * 4 + 1);            //           P_t(j) ready
         tc_fence_after();
         issue_PV(t, s, j == 0);
+        ATTN_PROF(8 + t * 4 + 2);            //           PV_t(j) issued
         if (more) {
           if (t == 0) {
             mbar_wait(&kv_full[s1], ((j + 1) / kStages) & 1);
             tc_fence_after();
           }
           issue_S(t, s1);       // overwrites P_t(j): the tensor pipe runs it after PV_t(j) above
+          ATTN_PROF(8 + t * 4 + 3);          //           S_t(j+1) issued
         }
       }
       if (elect_one()) {
@@ -227,10 +241,13 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     float m = 0.f, l = 0.f;
     for (int j = 0; j < kNT; ++j) {
+      if (warp == 2) ATTN_PROF(0);          // softmax warp 2 (tile 0): waiting for S_0(j)
       mbar_wait(&s_full[t], j & 1);         // S_t(j) complete; so is PV_t(j-1): P_t and O_t are ours
+      if (warp == 2) ATTN_PROF(1);          //   S_0(j) complete
       tc_fence_after();
       float sc[32];
       tmem_ld32(aS, sc);
+      if (warp == 2) ATTN_PROF(2);          //   S in registers
       if (j == kNT - 1) {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
@@ -262,12 +279,14 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       l += ls;
       m = m_use;
+      if (warp == 2) ATTN_PROF(3);          //   P computed (and O rescaled)
       tmem_st32(aS, ph);
       tmem_st32(aS + kKT, pl);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[t]);
+      if (warp == 2) ATTN_PROF(4);          //   P stored, p_ready signalled
     }
     mbar_wait(o_done, 0);
     tc_fence_after();
@@ -321,6 +340,23 @@ cudaError_t attention(const AttnArgs& a, cudaStream_t st) {
   dim3 grid(kTokP / 256, kHeads, a.nb);
   ast_attention_kernel<<<grid, kThreads, kSmemBytes, st>>>(tm[0], tm[1], tm[2], tm[3], a.q_hi, a.q_lo, a.o_hi, a.o_lo);
   return cudaGetLastError();
+}
+
+cudaError_t debug_profile(int enable, long long* host_out, int n) {
+  static long long* dbuf = nullptr;
+  cudaError_t e;
+  if (enable) {
+    if (!dbuf) {
+      if ((e = cudaMalloc(&dbuf, 64 * sizeof(long long))) != cudaSuccess) return e;
+    }
+    if ((e = cudaMemset(dbuf, 0, 64 * sizeof(long long))) != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(g_prof, &dbuf, sizeof(dbuf));
+  }
+  long long* null = nullptr;
+  if ((e = cudaMemcpyToSymbol(g_prof, &null, sizeof(null))) != cudaSuccess) return e;
+  if (dbuf && host_out && n > 0)
+    return cudaMemcpy(host_out, dbuf, sizeof(long long) * (n < 64 ? n : 64), cudaMemcpyDeviceToHost);
+  return cudaSuccess;
 }
 
 }  // namespace attn

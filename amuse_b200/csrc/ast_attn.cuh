@@ -25,5 +25,9 @@ inline size_t plane_elems(int nb) { return static_cast<size_t>(nb) * kHeads * kT
 
 cudaError_t attention(const AttnArgs& a, cudaStream_t st);
 
+// debug: enable != 0 arms a 64-slot clock64 timeline of CTA (0,0,0) for the next launches; enable == 0 disarms and
+// copies the stamps out (layout in ast_attn.cu)
+cudaError_t debug_profile(int enable, long long* host_out, int n);
+
 }  // namespace attn
 }  // namespace amuse
