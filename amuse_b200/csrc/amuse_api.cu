@@ -87,6 +87,18 @@ struct DecW {
   bool ready = false;
 };
 
+// ---- VAE encoder weights (MotionPrior.encode, vae.py:154-214): tcgen05 path only -----------
+struct EncLayerW {
+  size_t p_qkv, bqkv, p_wo, bo, p_w1, b1, p_w2, b2, ln1, ln2;   // planes (hi | lo) and fp32 vectors
+};
+struct EncW {
+  DevBuf arena;
+  EncLayerW L[9];
+  size_t p_skip[4], bskip[4];
+  size_t norm, p_embed, bembed, gtok, pe;   // skel_embedding planes are [128][352] (K zero-padded from 333)
+  bool ready = false;
+};
+
 struct DenW {
   DevBuf blob, misc;
   // offsets into misc
@@ -103,12 +115,14 @@ struct amuse_ctx {
   std::vector<float> alphas_cumprod;   // 1000 entries; default computed at create
   DenW den;
   DecW dec;
+  EncW enc;
   ast::Weights astw;
   std::map<std::tuple<int, int, int>, Schedule> schedules;   // (sampler, n_steps, eta bits)
   // workspaces
   DevBuf cond, lat_tmp, lat_out, one_coef;
   DevBuf dXA, dXB, dXC, dQKV, dO, dH, dSkip, dFeats, dCvec, dZero;
   DevBuf tX[3], tSkip, tO, tH;   // tcgen05 decoder path: activation planes (hi | lo halves)
+  DevBuf eFeat, eEmb;            // encoder: packed feature planes [rows][352] x 2, embedded frames [rows][128]
   bool dec_use_tc = true;        // decoder GEMMs on tcgen05 (3xTF32); false = fp32 FFMA kernels
   DevBuf h2d;   // staging for the *_host entry point
   DevBuf mel_t; // [257][128] mel filterbank weights (K-major)
@@ -515,6 +529,86 @@ int pack_decoder(amuse_ctx* ctx, cudaStream_t st) {
   return AMUSE_OK;
 }
 
+// -------------------------------------------------------------------- encoder packing
+int pack_encoder(amuse_ctx* ctx, cudaStream_t st) {
+  const std::string P = "vae.";
+  std::vector<float> ar;
+  auto put = [&](size_t n) {
+    size_t o = ar.size();
+    ar.resize(o + ((n + 3) & ~size_t(3)), 0.f);
+    return o;
+  };
+  auto put_planes = [&](const float* w, size_t n) {
+    const size_t o = put(2 * n);
+    tc::split_host(w, &ar[o], &ar[o + n], n);
+    return o;
+  };
+  auto put_vec = [&](const float* v, size_t n) {
+    const size_t o = put(n);
+    std::memcpy(&ar[o], v, n * 4);
+    return o;
+  };
+  EncW& d = ctx->enc;
+  for (int l = 0; l < 9; ++l) {
+    const std::string b = P + "encoder." + kBlocks[l];
+    NEED(inw, b + ".self_attn.in_proj_weight", 384, 128);
+    NEED(inb, b + ".self_attn.in_proj_bias", 384);
+    NEED(ow, b + ".self_attn.out_proj.weight", 128, 128);
+    NEED(ob, b + ".self_attn.out_proj.bias", 128);
+    NEED(w1, b + ".linear1.weight", 512, 128);
+    NEED(b1, b + ".linear1.bias", 512);
+    NEED(w2, b + ".linear2.weight", 128, 512);
+    NEED(b2, b + ".linear2.bias", 128);
+    EncLayerW& L = d.L[l];
+    L.p_qkv = put_planes(inw->data.data(), 384 * 128);
+    L.bqkv = put_vec(inb->data.data(), 384);
+    L.p_wo = put_planes(ow->data.data(), 128 * 128);
+    L.bo = put_vec(ob->data.data(), 128);
+    L.p_w1 = put_planes(w1->data.data(), 512 * 128);
+    L.b1 = put_vec(b1->data.data(), 512);
+    L.p_w2 = put_planes(w2->data.data(), 128 * 512);
+    L.b2 = put_vec(b2->data.data(), 128);
+    size_t* lns[2] = {&L.ln1, &L.ln2};
+    for (int q = 0; q < 2; ++q) {
+      NEED(nw, b + ".norm" + std::to_string(q + 1) + ".weight", 128);
+      NEED(nb, b + ".norm" + std::to_string(q + 1) + ".bias", 128);
+      *lns[q] = put(256);
+      std::memcpy(&ar[*lns[q]], nw->data.data(), 128 * 4);
+      std::memcpy(&ar[*lns[q] + 128], nb->data.data(), 128 * 4);
+    }
+  }
+  for (int i = 0; i < 4; ++i) {
+    const std::string sk = P + "encoder.linear_blocks." + std::to_string(i);
+    NEED(sw, sk + ".weight", 128, 256);
+    NEED(sb, sk + ".bias", 128);
+    d.p_skip[i] = put_planes(sw->data.data(), 128 * 256);
+    d.bskip[i] = put_vec(sb->data.data(), 128);
+  }
+  NEED(nw, P + "encoder.norm.weight", 128);
+  NEED(nb, P + "encoder.norm.bias", 128);
+  d.norm = put(256);
+  std::memcpy(&ar[d.norm], nw->data.data(), 128 * 4);
+  std::memcpy(&ar[d.norm + 128], nb->data.data(), 128 * 4);
+  NEED(ew, P + "skel_embedding.weight", 128, kFeats);
+  NEED(eb, P + "skel_embedding.bias", 128);
+  {   // [128][333] -> [128][352], zero-padded K, then planes
+    std::vector<float> wp(static_cast<size_t>(128) * 352, 0.f);
+    for (int n = 0; n < 128; ++n)
+      std::memcpy(&wp[static_cast<size_t>(n) * 352], ew->data.data() + static_cast<size_t>(n) * kFeats, kFeats * 4);
+    d.p_embed = put_planes(wp.data(), wp.size());
+  }
+  d.bembed = put_vec(eb->data.data(), 128);
+  NEED(gt, P + "global_motion_token", 2, 128);
+  d.gtok = put_vec(gt->data.data(), 256);
+  NEED(pe, P + "query_pos_encoder.pe", 500, 1, 128);
+  d.pe = put_vec(pe->data.data(), 500 * 128);
+  CU(d.arena.ensure(ar.size()));
+  CU(cudaMemcpyAsync(d.arena.p, ar.data(), ar.size() * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  d.ready = true;
+  return AMUSE_OK;
+}
+
 bool any_with_prefix(amuse_ctx* ctx, const char* pre) {
   const size_t n = std::strlen(pre);
   for (auto& kv : ctx->raw)
@@ -797,6 +891,117 @@ int run_decode_tc(amuse_ctx* ctx, int B, const float* latents, float* feats6d, f
   return AMUSE_OK;
 }
 
+// MotionPrior.encode (vae.py:154-214) on the same tcgen05 GEMMs as the decoder: skel_embedding
+// (K padded 333 -> 352), [2 global tokens | 300 frames] + learned PE, 9 post-LN encoder layers with
+// U-Net skips over 302 tokens, encoder.norm, then mu = token 0, logvar = token 1.
+int run_encode_tc(amuse_ctx* ctx, int B, const float* feats, float* mu, float* logvar, cudaStream_t st) {
+  using namespace dec;
+  constexpr int T = 302;
+  EncW& d = ctx->enc;
+  const float* W = d.arena.p;
+  const int chunk = ctx->dec_chunk;
+  const size_t Mc = static_cast<size_t>(std::min(B, chunk)) * T;
+  const size_t n128 = Mc * 128;
+  for (int i = 0; i < 3; ++i) CU(ctx->tX[i].ensure(2 * n128));
+  CU(ctx->tSkip.ensure(2 * n128 * 4));
+  CU(ctx->tO.ensure(2 * n128));
+  CU(ctx->tH.ensure(2 * Mc * 512));
+  CU(ctx->dQKV.ensure(Mc * 384));
+  CU(ctx->eFeat.ensure(2 * Mc * 352));
+  CU(ctx->eEmb.ensure(n128));
+  if (!ctx->dZero.p) {
+    CU(ctx->dZero.ensure(128));
+    CU(cudaMemset(ctx->dZero.p, 0, 128 * sizeof(float)));
+  }
+  struct P {
+    float* hi;
+    float* lo;
+  };
+  auto planes = [&](DevBuf& b, size_t n, size_t idx = 0) { return P{b.p + idx * 2 * n, b.p + idx * 2 * n + n}; };
+  const P XA = planes(ctx->tX[0], n128), XB = planes(ctx->tX[1], n128), XC = planes(ctx->tX[2], n128);
+  const P O = planes(ctx->tO, n128), H = planes(ctx->tH, Mc * 512);
+  auto SK = [&](int i) { return planes(ctx->tSkip, n128, static_cast<size_t>(i)); };
+
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nb = std::min(chunk, B - b0);
+    const int Mf = nb * kFrames, M = nb * T;
+    // skel_embedding on the 300 frames of every clip (vae.py:169)
+    float* fh = ctx->eFeat.p;
+    float* fl = ctx->eFeat.p + static_cast<size_t>(Mf) * 352;
+    CU(launch_pack_feats(feats + static_cast<size_t>(b0) * kFrames * kFeats, Mf, fh, fl, st));
+    tc::GemmDesc g{};
+    g.A_hi = fh; g.A_lo = fl; g.lda = 352;
+    g.W_hi = W + d.p_embed; g.W_lo = g.W_hi + 128 * 352; g.ldw = 352;
+    g.M = Mf; g.N = 128; g.K = 352; g.bias = W + d.bembed;
+    g.C = ctx->eEmb.p; g.ldc = 128;
+    CU(tc::gemm(tc::EPI_PLAIN, g, st));
+    // xseq = cat(global_motion_token, x) + query_pos_encoder.pe[:302]  (vae.py:176-191)
+    CU(launch_encoder_tokens(ctx->eEmb.p, W + d.gtok, W + d.pe, nb, XB.hi, XB.lo, st));
+    ctx->launches += 3;
+    P cur = XB;
+    for (int l = 0; l < 9; ++l) {
+      const EncLayerW& L = d.L[l];
+      if (l >= 5) {   // x = Linear(cat(x, xs.pop()))   (cross_attention.py:54-57)
+        const P sk = SK(8 - l);
+        g = tc::GemmDesc{};
+        g.A_hi = cur.hi; g.A_lo = cur.lo; g.lda = 128;
+        g.A2_hi = sk.hi; g.A2_lo = sk.lo; g.lda2 = 128; g.k_split = 128;
+        g.W_hi = W + d.p_skip[l - 5]; g.W_lo = g.W_hi + 128 * 256; g.ldw = 256;
+        g.M = M; g.N = 128; g.K = 256; g.bias = W + d.bskip[l - 5];
+        g.C_hi = XC.hi; g.C_lo = XC.lo; g.ldc = 128;
+        CU(tc::gemm(tc::EPI_PLANES, g, st));
+        ctx->launches++;
+        cur = XC;
+      }
+      g = tc::GemmDesc{};
+      g.A_hi = cur.hi; g.A_lo = cur.lo; g.lda = 128;
+      g.W_hi = W + L.p_qkv; g.W_lo = g.W_hi + 384 * 128; g.ldw = 128;
+      g.M = M; g.N = 384; g.K = 128; g.bias = W + L.bqkv;
+      g.C = ctx->dQKV.p; g.ldc = 384; g.q_cols = 128; g.q_scale = 0.17677669529663687f;
+      CU(tc::gemm(tc::EPI_QKV, g, st));
+      CU(launch_self_attention_planes(ctx->dQKV.p, O.hi, O.lo, nb, T, st));
+      // y = norm1(x + out_proj(o))
+      g = tc::GemmDesc{};
+      g.A_hi = O.hi; g.A_lo = O.lo; g.lda = 128;
+      g.W_hi = W + L.p_wo; g.W_lo = g.W_hi + 128 * 128; g.ldw = 128;
+      g.M = M; g.N = 128; g.K = 128; g.bias = W + L.bo;
+      g.R_hi = cur.hi; g.R_lo = cur.lo; g.ldr = 128;
+      g.ln_g = W + L.ln1; g.ln_b = W + L.ln1 + 128;
+      g.C_hi = XA.hi; g.C_lo = XA.lo; g.ldc = 128;
+      CU(tc::gemm(tc::EPI_RES_LN_PLANES, g, st));
+      // h = gelu(linear1(y))
+      g = tc::GemmDesc{};
+      g.A_hi = XA.hi; g.A_lo = XA.lo; g.lda = 128;
+      g.W_hi = W + L.p_w1; g.W_lo = g.W_hi + 512 * 128; g.ldw = 128;
+      g.M = M; g.N = 512; g.K = 128; g.bias = W + L.b1;
+      g.C_hi = H.hi; g.C_lo = H.lo; g.ldc = 512;
+      CU(tc::gemm(tc::EPI_GELU_PLANES, g, st));
+      // out = norm2(y + linear2(h))  [+ encoder.norm after the last block]
+      const P out = (l < 4) ? SK(l) : XB;
+      g = tc::GemmDesc{};
+      g.A_hi = H.hi; g.A_lo = H.lo; g.lda = 512;
+      g.W_hi = W + L.p_w2; g.W_lo = g.W_hi + 128 * 512; g.ldw = 512;
+      g.M = M; g.N = 128; g.K = 512; g.bias = W + L.b2;
+      g.R_hi = XA.hi; g.R_lo = XA.lo; g.ldr = 128;
+      g.ln_g = W + L.ln2; g.ln_b = W + L.ln2 + 128;
+      g.C_hi = out.hi; g.C_lo = out.lo; g.ldc = 128;
+      if (l == 8) {
+        g.cvec = ctx->dZero.p; g.rows_per_clip = 1 << 30;
+        g.ln2_g = W + d.norm; g.ln2_b = W + d.norm + 128;
+        CU(tc::gemm(tc::EPI_RES_LN_CROSS_LN_PLANES, g, st));
+      } else {
+        CU(tc::gemm(tc::EPI_RES_LN_PLANES, g, st));
+      }
+      ctx->launches += 5;
+      cur = out;
+    }
+    CU(launch_encoder_dist(cur.hi, cur.lo, nb, mu + static_cast<size_t>(b0) * 128,
+                           logvar + static_cast<size_t>(b0) * 128, st));
+    ctx->launches++;
+  }
+  return AMUSE_OK;
+}
+
 int run_decode_any(amuse_ctx* ctx, int B, const float* latents, float* feats6d, float* poses, float* trans,
                    cudaStream_t st) {
   return ctx->dec_use_tc ? run_decode_tc(ctx, B, latents, feats6d, poses, trans, st)
@@ -846,7 +1051,7 @@ void amuse_destroy(amuse_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->den.blob, &ctx->den.misc, &ctx->dec.arena, &ctx->cond, &ctx->lat_tmp, &ctx->lat_out,
                     &ctx->one_coef, &ctx->dXA, &ctx->dXB, &ctx->dXC, &ctx->dQKV, &ctx->dO, &ctx->dH, &ctx->dSkip,
                     &ctx->dFeats, &ctx->dCvec, &ctx->dZero, &ctx->h2d, &ctx->tX[0], &ctx->tX[1], &ctx->tX[2],
-                    &ctx->tSkip, &ctx->tO, &ctx->tH, &ctx->mel_t};
+                    &ctx->tSkip, &ctx->tO, &ctx->tH, &ctx->mel_t, &ctx->enc.arena, &ctx->eFeat, &ctx->eEmb};
   for (DevBuf* b : bufs) b->release();
   ast::release(ctx->astw);
   if (ctx->d_prof) cudaFree(ctx->d_prof);
@@ -876,10 +1081,7 @@ int amuse_load_weights(amuse_ctx* ctx, const char* name, const void* data, const
   }
   if (key.compare(0, 9, "denoiser.") != 0 && key.compare(0, 4, "vae.") != 0)
     return fail(ctx, AMUSE_E_INVALID, "unknown weight namespace in '%s'", name);
-  if (key.compare(0, 12, "vae.encoder.") == 0 || key == "vae.global_motion_token" ||
-      key.compare(0, 19, "vae.skel_embedding.") == 0 || key == "vae.query_pos_encoder.pe" ||
-      key == "denoiser.mem_pos.pe")
-    return AMUSE_OK;   // not on the sampling path
+  if (key == "denoiser.mem_pos.pe") return AMUSE_OK;   // never read by the reference's forward (denoiser.py:174-188)
   HostTensor t;
   t.shape.assign(shape, shape + ndim);
   t.data.resize(static_cast<size_t>(n));
@@ -899,6 +1101,10 @@ int amuse_finalize_weights(amuse_ctx* ctx, void* stream) {
   }
   if (find(ctx, "vae.decoder.norm.weight")) {
     if (int rc = pack_decoder(ctx, st)) return rc;
+    any = true;
+  }
+  if (find(ctx, "vae.encoder.norm.weight")) {   // optional: only the edit path (MotionPrior.encode) needs it
+    if (int rc = pack_encoder(ctx, st)) return rc;
     any = true;
   }
   if (ast::staged(ctx->astw)) {
@@ -978,6 +1184,24 @@ int amuse_decode(amuse_ctx* ctx, int B, const float* latents, float* feats6d, fl
   if (B < 1 || !latents || (!feats6d && !poses)) return fail(ctx, AMUSE_E_INVALID, "bad argument");
   cudaSetDevice(ctx->device);
   return run_decode_any(ctx, B, latents, feats6d, poses, trans, static_cast<cudaStream_t>(stream));
+}
+
+int amuse_encode(amuse_ctx* ctx, int B, const float* feats, float* mu, float* logvar, void* stream) {
+  if (!ctx) return AMUSE_E_INVALID;
+  if (!ctx->enc.ready) return fail(ctx, AMUSE_E_STATE, "vae encoder weights not finalized");
+  if (B < 1 || !feats || !mu || !logvar) return fail(ctx, AMUSE_E_INVALID, "bad argument");
+  cudaSetDevice(ctx->device);
+  return run_encode_tc(ctx, B, feats, mu, logvar, static_cast<cudaStream_t>(stream));
+}
+
+int amuse_motion_to_feats(amuse_ctx* ctx, int64_t n_frames, const float* poses, const float* trans, float* feats,
+                          void* stream) {
+  if (!ctx || n_frames < 0 || !poses || !trans || !feats) return fail(ctx, AMUSE_E_INVALID, "bad argument");
+  if (n_frames == 0) return AMUSE_OK;
+  cudaSetDevice(ctx->device);
+  CU(launch_motion_to_feats(poses, trans, n_frames, feats, static_cast<cudaStream_t>(stream)));
+  ctx->launches++;
+  return AMUSE_OK;
 }
 
 int amuse_rot6d_to_axis_angle(amuse_ctx* ctx, int64_t n, const float* d6, float* axis_angle, void* stream) {

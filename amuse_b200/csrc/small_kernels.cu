@@ -138,6 +138,95 @@ cudaError_t launch_add_planes(const float* hi, const float* lo, float* out, size
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- MotionPrior.encode side
+// axis-angle -> quaternion -> matrix -> first two rows (dm/utils/transforms.py:228-257, 96-124, 211-226),
+// same operation order as the reference in fp32
+__global__ void __launch_bounds__(256) motion_to_feats_kernel(const float* __restrict__ poses,
+                                                              const float* __restrict__ trans, long long n_frames,
+                                                              float* __restrict__ feats) {
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= n_frames * 56) return;
+  const long long f = gid / 56;
+  const int j = static_cast<int>(gid - f * 56);
+  float* dst = feats + f * 333;
+  if (j == 55) {
+    dst[330] = trans[f * 3 + 0];
+    dst[331] = trans[f * 3 + 1];
+    dst[332] = trans[f * 3 + 2];
+    return;
+  }
+  const float* a = poses + (f * 55 + j) * 3;
+  const float x = a[0], y = a[1], z = a[2];
+  const float ang = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+  const float half = 0.5f * ang;
+  const float sh = (fabsf(ang) < 1e-6f) ? (0.5f - __fmul_rn(ang, ang) / 48.0f) : __fdiv_rn(sinf(half), ang);
+  const float r = cosf(half), i = __fmul_rn(x, sh), jq = __fmul_rn(y, sh), k = __fmul_rn(z, sh);
+  const float nn = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r, r), __fmul_rn(i, i)), __fmul_rn(jq, jq)), __fmul_rn(k, k));
+  const float two_s = __fdiv_rn(2.0f, nn);
+  dst[j * 6 + 0] = 1.0f - __fmul_rn(two_s, __fadd_rn(__fmul_rn(jq, jq), __fmul_rn(k, k)));
+  dst[j * 6 + 1] = __fmul_rn(two_s, __fsub_rn(__fmul_rn(i, jq), __fmul_rn(k, r)));
+  dst[j * 6 + 2] = __fmul_rn(two_s, __fadd_rn(__fmul_rn(i, k), __fmul_rn(jq, r)));
+  dst[j * 6 + 3] = __fmul_rn(two_s, __fadd_rn(__fmul_rn(i, jq), __fmul_rn(k, r)));
+  dst[j * 6 + 4] = 1.0f - __fmul_rn(two_s, __fadd_rn(__fmul_rn(i, i), __fmul_rn(k, k)));
+  dst[j * 6 + 5] = __fmul_rn(two_s, __fsub_rn(__fmul_rn(jq, k), __fmul_rn(i, r)));
+}
+cudaError_t launch_motion_to_feats(const float* poses, const float* trans, long long n_frames, float* feats,
+                                   cudaStream_t st) {
+  const long long total = n_frames * 56;
+  motion_to_feats_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(poses, trans, n_frames, feats);
+  return cudaGetLastError();
+}
+
+__device__ __forceinline__ void split_rna(float x, float& hi, float& lo) {
+  uint32_t h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  lo = x - hi;
+}
+
+__global__ void __launch_bounds__(352) pack_feats_kernel(const float* __restrict__ feats, float* __restrict__ hi,
+                                                         float* __restrict__ lo) {
+  const long long row = blockIdx.x;
+  const int c = threadIdx.x;
+  const float v = (c < 333) ? feats[row * 333 + c] : 0.f;
+  float h, l;
+  split_rna(v, h, l);
+  hi[row * 352 + c] = h;
+  lo[row * 352 + c] = l;
+}
+cudaError_t launch_pack_feats(const float* feats, long long rows, float* hi, float* lo, cudaStream_t st) {
+  pack_feats_kernel<<<static_cast<unsigned>(rows), 352, 0, st>>>(feats, hi, lo);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(128) encoder_tokens_kernel(const float* __restrict__ emb, const float* __restrict__ gtok,
+                                                             const float* __restrict__ pe, float* __restrict__ hi,
+                                                             float* __restrict__ lo) {
+  const int row = blockIdx.x, c = threadIdx.x;      // row = clip * 302 + token
+  const int b = row / 302, tok = row - b * 302;
+  const float v = (tok < 2) ? gtok[tok * 128 + c] : emb[(static_cast<size_t>(b) * 300 + tok - 2) * 128 + c];
+  float h, l;
+  split_rna(v + pe[tok * 128 + c], h, l);
+  hi[static_cast<size_t>(row) * 128 + c] = h;
+  lo[static_cast<size_t>(row) * 128 + c] = l;
+}
+cudaError_t launch_encoder_tokens(const float* emb, const float* gtok, const float* pe, int nb, float* hi, float* lo,
+                                  cudaStream_t st) {
+  encoder_tokens_kernel<<<nb * 302, 128, 0, st>>>(emb, gtok, pe, hi, lo);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) encoder_dist_kernel(const float* __restrict__ hi, const float* __restrict__ lo,
+                                                           float* __restrict__ mu, float* __restrict__ logvar) {
+  const int b = blockIdx.x, t = threadIdx.x >> 7, c = threadIdx.x & 127;
+  const size_t src = (static_cast<size_t>(b) * 302 + t) * 128 + c;
+  (t ? logvar : mu)[b * 128 + c] = hi[src] + lo[src];
+}
+cudaError_t launch_encoder_dist(const float* hi, const float* lo, int nb, float* mu, float* logvar, cudaStream_t st) {
+  encoder_dist_kernel<<<nb, 256, 0, st>>>(hi, lo, mu, logvar);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_rot6d_flat(const float* d6, long long n, float* aa, cudaStream_t st) {
   rot6d_flat_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(d6, n, aa);
   return cudaGetLastError();

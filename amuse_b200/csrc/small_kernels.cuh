@@ -19,6 +19,18 @@ cudaError_t launch_rot6d(const float* feats, int feat_ld, long long n_frames, fl
                          cudaStream_t st);
 
 cudaError_t launch_rot6d_flat(const float* d6, long long n, float* aa, cudaStream_t st);
+
+// ---- MotionPrior.encode side (vae.py:154-214; infer_ldm.py:454-462)
+// poses [n_frames][55][3] axis-angle + trans [n_frames][3] -> feats [n_frames][333] (55 x 6D | trans)
+cudaError_t launch_motion_to_feats(const float* poses, const float* trans, long long n_frames, float* feats,
+                                   cudaStream_t st);
+// feats [rows][333] -> TF32 hi/lo planes [rows][352] (columns 333..351 zero): the K-padded A operand of skel_embedding
+cudaError_t launch_pack_feats(const float* feats, long long rows, float* hi, float* lo, cudaStream_t st);
+// xseq = cat(global_motion_token[2], emb[300]) + pe[:302] per clip -> planes [nb*302][128]
+cudaError_t launch_encoder_tokens(const float* emb, const float* gtok, const float* pe, int nb, float* hi, float* lo,
+                                  cudaStream_t st);
+// mu[b] = x[b*302 + 0], logvar[b] = x[b*302 + 1]  (hi + lo)
+cudaError_t launch_encoder_dist(const float* hi, const float* lo, int nb, float* mu, float* logvar, cudaStream_t st);
 cudaError_t launch_add_planes(const float* hi, const float* lo, float* out, size_t n, cudaStream_t st);
 
 }  // namespace amuse

@@ -137,6 +137,27 @@ class Engine:
                                               self._stream()))
         return (poses, trans, feats) if want_feats else (poses, trans)
 
+    def encode(self, feats: torch.Tensor):
+        """``MotionPrior.encode`` without the rsample draw: feats [B,300,333] -> (mu [B,128], logvar [B,128])."""
+        B = feats.shape[0]
+        x = self._dev(feats, (B, 300, 333))
+        mu, logvar = (torch.empty(B, 128, device=self.device, dtype=torch.float32) for _ in range(2))
+        with torch.cuda.device(self.device):
+            self._check(self.lib.amuse_encode(self._h, B, _ptr(x), _ptr(mu), _ptr(logvar), self._stream()))
+        return mu, logvar
+
+    def motion_to_feats(self, poses: torch.Tensor, trans: torch.Tensor) -> torch.Tensor:
+        """poses [...,55,3] axis-angle + trans [...,3] -> [...,333] (55 x 6D | trans), infer_ldm.py:454-461."""
+        p, t = self._dev(poses), self._dev(trans)
+        lead = tuple(p.shape[:-2])
+        if p.shape[-2:] != (55, 3) or tuple(t.shape) != lead + (3,):
+            raise ValueError("poses must be [...,55,3] and trans [...,3]")
+        n = p.numel() // 165
+        out = torch.empty(*lead, 333, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.amuse_motion_to_feats(self._h, n, _ptr(p), _ptr(t), _ptr(out), self._stream()))
+        return out
+
     def rot6d_to_axis_angle(self, d6: torch.Tensor) -> torch.Tensor:
         x = self._dev(d6)
         n = x.numel() // 6

@@ -273,7 +273,45 @@ def vae_decode(sd: SD, z: Tensor, nframes: int = 300) -> Tensor:
     return F.linear(x, sd["final_layer.weight"], sd["final_layer.bias"])
 
 
+# --------------------------------------------------------------------------- VAE encoder
+def vae_encode(sd: SD, feats: Tensor):
+    """Deterministic part of ``MotionPrior.encode`` (models/latent_diffusion/vae.py:154-214), arch
+    encoder_decoder, pe_type mld, MLP_DIST false, latent_size 1, all lengths = nframes (mask all-true):
+    feats [B,T,333] -> (mu [B,128], logvar [B,128]).  The reference then draws
+    ``latent = Normal(mu, exp(logvar)**0.5).rsample()`` from the global torch generator (vae.py:210-213);
+    that draw stays on the host side of the boundary."""
+    B = feats.shape[0]
+    x = F.linear(feats, sd["skel_embedding.weight"], sd["skel_embedding.bias"])        # vae.py:169
+    dist = sd["global_motion_token"][None].expand(B, -1, -1)                           # vae.py:176
+    xseq = torch.cat((dist, x), dim=1)                                                 # vae.py:185
+    xseq = xseq + sd["query_pos_encoder.pe"][: xseq.shape[1], 0, :][None]               # vae.py:191
+    out = skip_encoder(xseq, sd, "encoder")[:, :2]                                      # vae.py:192-193
+    return out[:, 0], out[:, 1]                                                         # vae.py:205-206
+
+
 # --------------------------------------------------------------------------- rotations
+def axis_angle_to_rot6d(aa: Tensor) -> Tensor:
+    """``matrix_to_rotation_6d(axis_angle_to_matrix(aa))`` (dm/utils/transforms.py:228-257 -> 96-124 ->
+    211-226): axis-angle [...,3] -> quaternion -> matrix -> first two rows [...,6]."""
+    ang = torch.norm(aa, p=2, dim=-1, keepdim=True)
+    half = 0.5 * ang
+    small = ang.abs() < 1e-6
+    s = torch.where(small, 0.5 - ang * ang / 48, torch.sin(half) / torch.where(small, torch.ones_like(ang), ang))
+    q = torch.cat([torch.cos(half), aa * s], dim=-1)
+    r, i, j, k = torch.unbind(q, -1)
+    two_s = 2.0 / (q * q).sum(-1)
+    return torch.stack((1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
+                        two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r)), -1)
+
+
+def motion_to_feats(poses: Tensor, trans: Tensor) -> Tensor:
+    """``_loader_helper_v1`` motion branch (infer_ldm.py:454-462): poses [B,T,55,3] axis-angle + trans
+    [B,T,3] -> the VAE's [B,T,333] feature layout (55 x 6D, then trans)."""
+    B, T = poses.shape[:2]
+    return torch.cat((axis_angle_to_rot6d(poses).reshape(B, T, 330), trans), dim=-1)
+
+
+
 def rotation_6d_to_matrix(d6: Tensor) -> Tensor:
     """Gram-Schmidt, rows (b1,b2,b3) (dm/utils/transforms.py:187-208; F.normalize eps 1e-12)."""
     a1, a2 = d6[..., :3], d6[..., 3:]

@@ -67,6 +67,19 @@ class RefPath:
         return feats, poses, feats[:, :, -3:]
 
 
+def synthetic_motion(B):
+    """Closed-form smooth SMPL-X motion (axis-angle up to ~0.9 rad, a few exactly-zero joints for the
+    small-angle branch): poses [B,300,55,3], trans [B,300,3]."""
+    b = torch.arange(B, dtype=torch.float64)[:, None, None, None]
+    t = torch.arange(300, dtype=torch.float64)[None, :, None, None]
+    j = torch.arange(55, dtype=torch.float64)[None, None, :, None]
+    c = torch.arange(3, dtype=torch.float64)[None, None, None, :]
+    poses = 0.5 * torch.sin(0.05 * t + 0.7 * j + 1.3 * c + b) + 0.2 * torch.cos(0.011 * t * (c + 1) - 0.3 * j)
+    poses[:, :, 7] = 0.0
+    trans = 0.1 * torch.cos(0.03 * t[:, :, 0] + c[:, :, 0] + b[:, :, 0])
+    return poses.to(torch.float32), trans.to(torch.float32)
+
+
 def randn(seed, *shape):
     return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
 
@@ -152,6 +165,21 @@ def main():
     aa32 = r32.tf.matrix_to_axis_angle(r32.tf.rotation_6d_to_matrix(d6))
     aa64 = r64.tf.matrix_to_axis_angle(r64.tf.rotation_6d_to_matrix(d6.double()))
     np.savez_compressed(OUT / "rot6d_cases.npz", d6=f32(d6), aa_f32=f32(aa32), aa_f64=f64(aa64), **meta)
+
+    # G8 -- MotionPrior.encode (section 8f rank 3) on closed-form motion (regenerated by the tests from the
+    # same formula: no input storage), through the reference's own axis-angle -> 6D conversion
+    poses, trans = synthetic_motion(2)
+    out = {}
+    for tag, r, cast in (("f32", r32, f32), ("f64", r64, f64)):
+        pz = r.c(poses)
+        rot6 = r.tf.matrix_to_rotation_6d(r.tf.axis_angle_to_matrix(pz)).reshape(2, 300, 330)    # infer_ldm.py:457-460
+        feats = torch.cat((rot6, r.c(trans)), dim=-1)
+        with torch.no_grad():
+            _, dist = r.vae.encode(feats, [300] * 2)                                               # vae.py:154-214
+        out[f"feats_{tag}"] = cast(feats[:, FRAME_IDX])
+        out[f"mu_{tag}"] = cast(dist.loc[0])
+        out[f"std_{tag}"] = cast(dist.scale[0])
+    np.savez_compressed(OUT / "encode_b2.npz", frame_idx=FRAME_IDX, **out, **meta)
 
     for p in sorted(OUT.glob("*.npz")):
         print(f"{p.name:32s} {p.stat().st_size/1024:8.1f} KiB")

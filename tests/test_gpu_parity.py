@@ -199,3 +199,35 @@ def test_decode_chunking_and_full_size(engine, synthetic_weights):
         assert torch.equal(f1[0], feats[b])
     ref = R.vae_decode(synthetic_weights["vae"], z[69:70])
     assert (feats[69].cpu() - ref[0]).abs().max().item() < TOL_FEATS
+
+
+def test_encode_golden(engine, golden_dir):
+    """axis-angle -> 6D features -> MotionPrior.encode (vae.py:154-214) against the
+    reference's own modules (tests/golden/encode_b2.npz, oracle/make_golden.py G8) on closed-form motion."""
+    from oracle.make_golden import synthetic_motion
+    g = np.load(golden_dir / "encode_b2.npz")
+    idx = g["frame_idx"]
+    poses, trans = synthetic_motion(2)
+    feats = engine.motion_to_feats(poses, trans)
+    e = (feats[:, idx].cpu().double() - _t(g["feats_f64"])).abs().max().item()
+    r = (_t(g["feats_f32"]).double() - _t(g["feats_f64"])).abs().max().item()
+    print(f"[parity] motion_to_feats: |cuda-f64|={e:.3e}  |ref32-f64|={r:.3e}")
+    assert e < max(2e-6, 4 * r)
+    mu, logvar = engine.encode(feats)
+    std = logvar.exp().pow(0.5)                                   # vae.py:210
+    e_mu, _, r_mu = _report("encode mu", mu, g["mu_f32"], g["mu_f64"])
+    e_sd, _, r_sd = _report("encode std", std, g["std_f32"], g["std_f64"])
+    assert e_mu < max(TOL_FEATS, 4 * r_mu) and e_sd < max(2 * TOL_FEATS, 4 * r_sd)   # |mu|, |std| up to ~4
+
+
+def test_encode_batch_and_chunking(engine, synthetic_weights):
+    """40 clips (two decoder-sized passes of 32 + 8) against the oracle; clip order must not matter."""
+    from oracle.make_golden import synthetic_motion
+    poses, trans = synthetic_motion(40)
+    feats = engine.motion_to_feats(poses, trans)
+    mu, logvar = engine.encode(feats)
+    ref_mu, ref_lv = R.vae_encode(synthetic_weights["vae"], R.motion_to_feats(poses[[0, 33, 39]], trans[[0, 33, 39]]))
+    assert (mu[[0, 33, 39]].cpu() - ref_mu).abs().max().item() < TOL_FEATS
+    assert (logvar[[0, 33, 39]].cpu() - ref_lv).abs().max().item() < 2 * TOL_FEATS
+    mu2, _ = engine.encode(feats.flip(0))
+    assert torch.equal(mu2.flip(0), mu)

@@ -111,3 +111,19 @@ def test_restatement_matches_reference_modules(sds):
         assert (R.vae_decode(v32, z) - ref).abs().max() < 2e-5
         d6 = ref[:, :, :-3].reshape(2, 300, 55, 6)
         assert torch.equal(R.rot6d_to_axis_angle(d6), tf.matrix_to_axis_angle(tf.rotation_6d_to_matrix(d6)))
+
+
+def test_encode_golden(golden_dir, sds):
+    """MotionPrior.encode restatement + axis-angle -> 6D against the reference-generated fixture."""
+    from oracle.make_golden import synthetic_motion
+    g = np.load(golden_dir / "encode_b2.npz")
+    poses, trans = synthetic_motion(2)
+    feats = R.motion_to_feats(poses, trans)
+    assert np.abs(feats[:, g["frame_idx"]].numpy() - g["feats_f32"]).max() < 1e-6
+    _, v32, _, v64 = sds
+    mu, lv = R.vae_encode(v32, feats)
+    assert np.abs(mu.numpy() - g["mu_f64"]).max() < 2e-5
+    assert np.abs(lv.exp().pow(0.5).numpy() - g["std_f64"]).max() < 2e-5
+    mu64, lv64 = R.vae_encode(v64, R.motion_to_feats(poses.double(), trans.double()))
+    assert np.abs(mu64.numpy() - g["mu_f64"]).max() < 1e-10
+    assert np.abs(lv64.exp().pow(0.5).numpy() - g["std_f64"]).max() < 1e-10
