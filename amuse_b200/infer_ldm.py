@@ -189,6 +189,7 @@ class PretrainedLPDM_v1:
         self.device = torch.device(device)
         self.diffonly, self.baseline = False, False
         self.smplx_rep, self.seq_len, self.train_pose_framelen = "6D", 300, 300
+        self.skip_trans = self.train_upper_body = False
         self.latent_dim = [1, 128]
         self.num_inference_timesteps, self.eta, self.sampler = num_inference_timesteps, eta, sampler
         self.target_length, self.norm_mean, self.norm_std, self.num_mel_bins = 1024, -9.173025, 5.062332, 128
@@ -257,11 +258,107 @@ class PretrainedLPDM_v1:
     def collect_audio_metrics(self, sliced_chunk, framerate=16000 // 2, baseline=False, tgtpath=None):
         raise NotImplementedError("fbank reconstruction metrics (AST_EVP fusion/decoder heads) are outside the sampling path")
 
-    # ------------------------------------------------------------------ edits (infer_ldm.py:225-414)
+    # ------------------------------------------------------------------ edits (infer_ldm.py:225-517)
+    def _loader_helper_v1(self, motion, audio):
+        """One (motion [T,168] axis-angle+trans, audio [C,N] 16 kHz) recording -> its latents
+        (infer_ldm.py:416-502): AST features of every 10 s audio chunk and the VAE latent of every
+        300-frame motion take, truncated to the number of takes.  All chunks / takes go through the
+        engine as one batch."""
+        if self.baseline:
+            raise NotImplementedError
+        if self.smplx_rep != "6D":
+            raise NotImplementedError("only the released 6D SMPL-X representation is supported")
+        total_chunks = audio.shape[1] // 160000
+        # NB the reference slices chunk k as audio[:, k:k+160000] (offset k SAMPLES, infer_ldm.py:421-422);
+        # kept as is.  Channel 0 = kaldi's channel=-1.
+        waves = torch.stack([audio[0, k:k + 160000] for k in range(total_chunks)], dim=0)
+        if self.device_fbank:
+            fbank = self.engine.fbank(waves.to(self.device), self.norm_mean, self.norm_std)
+        else:
+            fbank = torch.stack([self._fbank(w[None]) for w in waves], dim=0)
+        audio_con, audio_emo, audio_sty = self.engine.ast_features(fbank)
+
+        L = self.train_pose_framelen
+        takes = motion.shape[0] // L
+        mb = motion[: takes * L].reshape(takes, L, -1).to(self.device, torch.float32)
+        feats = self.engine.motion_to_feats(mb[:, :, :-3].reshape(takes, L, 55, 3), mb[:, :, -3:])   # infer_ldm.py:454-461
+        mu, logvar = self.engine.encode(feats)
+        # MotionPrior.encode's tail (vae.py:209-213): Normal(mu, exp(logvar)**0.5).rsample(), global generator
+        std = logvar.exp().pow(0.5)
+        eps = torch.empty((1, takes, mu.shape[-1]), device=self.device, dtype=torch.float32).normal_()
+        z_motion = (mu[None] + eps * std[None]).squeeze()                                             # infer_ldm.py:462
+        n = z_motion.shape[0]
+        return {"z_motion": z_motion, "z_con": audio_con[:n], "z_emo": audio_emo[:n], "z_sty": audio_sty[:n]}
+
+    def _encode_take(self, data, actor, take):
+        """Fill ld_z / ld_z_con / ld_z_emo / ld_z_sty of one (actor, take) entry in place."""
+        entry = data[actor][take]
+        motion = torch.from_numpy(entry["ld_motion"]).to(self.device)
+        z = self._loader_helper_v1(motion, entry["ld_waveform"])
+        entry["ld_z"], entry["ld_z_con"] = z["z_motion"], z["z_con"]
+        entry["ld_z_emo"], entry["ld_z_sty"] = z["z_emo"], z["z_sty"]
+
+    @staticmethod
+    def _actors_of(info):
+        a, b = info.split("_")[0][1:-1].split("-")[:2]
+        return a, b
+
     def process_loader(self, data_dict) -> Dict:
-        """Dataset-driven edit preparation.  With no edit flag set (the shipped ``edit_gesture`` default,
-        scripts/overrides/edit_gesture.yaml) the reference returns an empty dict; the dataset-driven
-        branches need ``MotionPrior.encode`` and BEAT data."""
-        if self.style_Xemo_transfer or self.style_transfer or self.emotion_control:
-            raise NotImplementedError("dataset-driven edits need MotionPrior.encode (not on the sampling path yet)")
-        return dict()
+        """Dataset-driven edit preparation (infer_ldm.py:225-414): encodes every recording the edit needs
+        and cross-links the emotion / style latents exactly as the reference does (same dict keys).  With
+        no edit flag set (the shipped ``edit_gesture`` default) the result is an empty dict."""
+        loader_data = dict()
+        if (self.style_Xemo_transfer or self.style_transfer or self.emotion_control) and \
+                (self.skip_trans or self.train_upper_body):
+            raise NotImplementedError("skip_trans / upper-body ablations are not part of the released configuration")
+
+        if self.style_Xemo_transfer:          # two actors, two emotions, emotion AND style swapped across actors
+            info, data = data_dict["style_Xemo_transfer_info"], data_dict["style_Xemo_transfer"]
+            if "," in info:
+                raise NotImplementedError("Multiple style transfer not implemented yet")
+            a1, a2 = self._actors_of(info)
+            t1, t2, t3, t4 = ("_".join(part.split("_")[2:]) for part in info.split("*")[1:5])
+            assert t1 == t3 and t2 == t4, "Takes are not the same for style transfer!"
+            for t in (t1, t2):
+                assert data[a1][t]["ld_emo_label"] == data[a2][t]["ld_emo_label"], \
+                    f"Emotion labels are not the same for style transfer! {data[a1][t]['ld_emo_label']} != {data[a2][t]['ld_emo_label']}"
+            for actor, take in ((a1, t1), (a2, t3), (a1, t2), (a2, t4)):
+                self._encode_take(data, actor, take)
+            for (ra, rt), (sa, st) in (((a1, t1), (a2, t4)), ((a2, t3), (a1, t2)), ((a1, t2), (a2, t3)), ((a2, t4), (a1, t1))):
+                data[ra][rt][f"ld_z_emo_{sa}_{st}"] = data[sa][st]["ld_z_emo"]
+                data[ra][rt][f"ld_z_sty_{sa}_{st}"] = data[sa][st]["ld_z_sty"]
+            data["takes"] = f"{t1}*{t2}*{t3}*{t4}"
+            loader_data["style_Xemo_transfer"] = data
+
+        if self.style_transfer:               # two actors, same emotion, two takes
+            info, data = data_dict["style_transfer_info"], data_dict["style_transfer"]
+            if "," in info:
+                raise NotImplementedError("Multiple style transfer not implemented yet")
+            a1, a2 = self._actors_of(info)
+            t1, t2 = mapinfo2takes(info)[:2]
+            labels = {data[a][t]["ld_emo_label"] for a in (a1, a2) for t in (t1, t2)}
+            assert len(labels) == 1, "Emotion labels are not the same for style transfer!"
+            for actor, take in ((a1, t1), (a2, t1), (a1, t2), (a2, t2)):
+                self._encode_take(data, actor, take)
+            for t in (t1, t2):
+                for ra, sa in ((a1, a2), (a2, a1)):
+                    # (the reference stores the donor's EMOTION latent under the *_sty_* key and vice versa,
+                    #  infer_ldm.py:371-381; kept)
+                    data[ra][t][f"ld_z_sty_{sa}"] = data[sa][t]["ld_z_emo"]
+                    data[ra][t][f"ld_z_emo_{sa}"] = data[sa][t]["ld_z_sty"]
+            loader_data["style_transfer"] = data
+
+        if self.emotion_control:              # one actor, several takes: every take gets the others' emotion latents
+            info, data = data_dict["emotion_control_info"], data_dict["emotion_control"]
+            if "," in info:
+                raise NotImplementedError("Emotion control with multiple actors or multiple content emotions not implemented yet")
+            for actor in data.keys():
+                for take in data[actor].keys():
+                    self._encode_take(data, actor, take)
+            for actor in data.keys():
+                for take in data[actor].keys():
+                    for other in data[actor].keys():
+                        if other != take:
+                            data[actor][take][f"ld_z_emo_{other}"] = data[actor][other]["ld_z_emo"]
+            loader_data["emotion_control"] = data
+        return loader_data

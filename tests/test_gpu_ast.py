@@ -52,3 +52,54 @@ def test_process_single_seq_shapes_and_fbank():
     out = m.diffusion_backward(1, con, emo, sty)
     assert out["poses"].shape == (1, 300, 55, 3) and torch.isfinite(out["poses"]).all()
     m.engine.close()
+
+
+def test_process_loader_style_xemo_transfer():
+    """Config 5 (edit_gesture, style_Xemo_transfer): the dataset-driven edit preparation of the mirror class
+    (reference infer_ldm.py:225-323, 416-502) on a synthetic data_dict: dict contract, the cross-links, and the
+    latents against the oracle (AST features of the reference's chunk slicing; VAE latent with the same draw)."""
+    from amuse_b200.infer_ldm import PretrainedLPDM_v1
+    from oracle import lpdm_ref as R
+    from oracle.make_golden import synthetic_motion
+    den, vae, ast = W.denoiser_state_dict(), W.motionprior_state_dict(), W.ast_state_dict(depth=1)
+    m = PretrainedLPDM_v1.from_state_dicts(den, vae, ast, device="cuda:0")
+    m.style_Xemo_transfer = True
+    poses, trans = synthetic_motion(4)                                   # 4 recordings x 300 frames
+    g = torch.Generator().manual_seed(5)
+
+    def rec(i, label):
+        motion = torch.cat((poses[i].reshape(300, 165), trans[i]), dim=1)
+        motion = torch.cat((motion, motion.flip(0)), dim=0)               # 600 frames = 2 takes of 300
+        return {"ld_motion": motion.numpy(), "ld_waveform": 0.1 * torch.randn(1, 320000 + 123, generator=g),
+                "ld_emo_label": label}
+
+    t_ang, t_hap = "0_73_73", "0_65_65"
+    data = {"lu": {t_ang: rec(0, "angry"), t_hap: rec(1, "happy")},
+            "lawrence": {t_ang: rec(2, "angry"), t_hap: rec(3, "happy")}}
+    info = f"[lu-lawrence]_[angry-happy]_*lu_angry_{t_ang}*lu_happy_{t_hap}*lawrence_angry_{t_ang}*lawrence_happy_{t_hap}*"
+    torch.manual_seed(123)
+    out = m.process_loader({"style_Xemo_transfer_info": info, "style_Xemo_transfer": data})["style_Xemo_transfer"]
+    assert out["takes"] == f"{t_ang}*{t_hap}*{t_ang}*{t_hap}"
+    e = out["lu"][t_ang]
+    assert e["ld_z"].shape == (2, 128) and e["ld_z_con"].shape == (2, 256) and e["ld_z"].is_cuda
+    # cross-links (infer_ldm.py:308-318): lu/angry gets lawrence/happy's emotion + style, and so on
+    assert e[f"ld_z_emo_lawrence_{t_hap}"] is out["lawrence"][t_hap]["ld_z_emo"]
+    assert e[f"ld_z_sty_lawrence_{t_hap}"] is out["lawrence"][t_hap]["ld_z_sty"]
+    assert out["lawrence"][t_hap][f"ld_z_emo_lu_{t_ang}"] is e["ld_z_emo"]
+    assert out["lu"][t_hap][f"ld_z_sty_lawrence_{t_ang}"] is out["lawrence"][t_ang]["ld_z_sty"]
+    # AST features: chunk k of the reference is audio[:, k:k+160000]
+    wav = data["lu"][t_ang]["ld_waveform"]
+    fb = torch.stack([A.fbank_features(wav[:, k:k + 160000]) for k in range(2)])
+    rc, re, rs = A.ast_features(ast, fb)
+    assert (e["ld_z_con"].cpu() - rc).abs().max().item() < 3e-4
+    assert (e["ld_z_sty"].cpu() - rs).abs().max().item() < 3e-4
+    # VAE latent: first recording encoded first, so its draw is the first one after the seed
+    motion = torch.from_numpy(data["lu"][t_ang]["ld_motion"]).view(2, 300, 168)
+    mu, lv = R.vae_encode(vae, R.motion_to_feats(motion[:, :, :165].reshape(2, 300, 55, 3), motion[:, :, 165:]))
+    torch.manual_seed(123)
+    eps = torch.empty((1, 2, 128), device="cuda:0").normal_().cpu()[0]
+    assert (e["ld_z"].cpu() - (mu + eps * lv.exp().pow(0.5))).abs().max().item() < 2e-4
+    # the swapped conditions drive the sampler like any others (trainer.py:552-605)
+    res = m.diffusion_backward(2, e["ld_z_con"], e[f"ld_z_emo_lawrence_{t_hap}"], e[f"ld_z_sty_lawrence_{t_hap}"])
+    assert res["poses"].shape == (2, 300, 55, 3) and torch.isfinite(res["poses"]).all()
+    m.engine.close()
