@@ -46,6 +46,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly one JSON line: everything else that native libraries write to fd 1 (NCCL prints its
+# version banner there) is sent to stderr; emit() writes to the saved descriptor.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def synth_inputs(B, seed_base=0):
     """BASELINE.md / SURVEY D1 config 3: z_* ~ N(0,1) [B,256] seed 3, latents0 [B,128] seed 1."""
     g1 = torch.Generator().manual_seed(1 + seed_base)
@@ -179,7 +190,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- CUDA arm
@@ -437,7 +448,7 @@ def run_ours(args, rank, world, local_rank):
         "scope_E": scope_e,
         "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -459,7 +470,6 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
     try:
         run_ours(args, rank, world, local_rank)
