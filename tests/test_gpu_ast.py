@@ -103,3 +103,18 @@ def test_process_loader_style_xemo_transfer():
     res = m.diffusion_backward(2, e["ld_z_con"], e[f"ld_z_emo_lawrence_{t_hap}"], e[f"ld_z_sty_lawrence_{t_hap}"])
     assert res["poses"].shape == (2, 300, 55, 3) and torch.isfinite(res["poses"]).all()
     m.engine.close()
+
+
+def test_ast_batch_invariance_two_passes():
+    """33 clips = two passes (17 + 16) of the AST stack: every clip's features equal its own single-clip run
+    (per-row GEMM / per-(clip, head) attention: no cross-clip arithmetic), and the zero pad rows / columns of
+    the q / k / v^T planes stay clean across passes."""
+    eng, sd = _engine_with_ast(1)
+    fb = torch.randn(33, 1024, 128, generator=torch.Generator().manual_seed(3)) * 0.5
+    fb[7] *= 40.0                                              # a loud clip must not leak into its neighbours
+    con, emo, sty = eng.ast_features(fb)
+    for i in (0, 6, 8, 16, 17, 32):
+        c1, e1, s1 = eng.ast_features(fb[i:i + 1])
+        assert torch.equal(c1[0], con[i]) and torch.equal(e1[0], emo[i]) and torch.equal(s1[0], sty[i])
+    assert torch.isfinite(con).all() and torch.isfinite(sty).all()
+    eng.close()

@@ -231,3 +231,43 @@ def test_encode_batch_and_chunking(engine, synthetic_weights):
     assert (logvar[[0, 33, 39]].cpu() - ref_lv).abs().max().item() < 2 * TOL_FEATS
     mu2, _ = engine.encode(feats.flip(0))
     assert torch.equal(mu2.flip(0), mu)
+
+
+def test_full_size_edit_permutation_equivariance(engine):
+    """BASELINE configs[4] (edit_gesture, B=256) through a size-independent property: clips are independent
+    (SURVEY 8e), so permuting the (content, emotion, style, noise) rows -- what style_Xemo_transfer does with the
+    emotion/style banks -- permutes the poses bit for bit, and any clip equals its own B=1 run."""
+    B = 256
+    g = torch.Generator().manual_seed(4)
+    l0, con, emo, sty = (torch.randn(B, d, generator=g) for d in (128, 256, 256, 256))
+    perm = torch.randperm(B, generator=g)
+    a = engine.diffusion_backward(l0, con, emo, sty, n_steps=50, sampler="ddim", want_latents=True)
+    b = engine.diffusion_backward(l0[perm], con[perm], emo[perm], sty[perm], n_steps=50, sampler="ddim", want_latents=True)
+    assert torch.equal(a["latents"][perm], b["latents"]) and torch.equal(a["poses"][perm], b["poses"])
+    assert torch.isfinite(a["poses"]).all() and torch.equal(a["trans"][perm], b["trans"])
+    # swapping only the emotion/style rows changes exactly the clips whose rows changed
+    emo2 = emo.clone()
+    emo2[:128] = emo[perm[:128]]
+    c = engine.diffusion_backward(l0, con, emo2, sty, n_steps=50, sampler="ddim", want_latents=True)
+    same_row = (emo2 == emo).all(dim=1)
+    assert torch.equal(c["latents"][same_row], a["latents"][same_row])
+    assert not torch.equal(c["latents"][~same_row], a["latents"][~same_row])
+    one = engine.diffusion_backward(l0[200:201], con[200:201], emo[200:201], sty[200:201], n_steps=50, sampler="ddim",
+                                    want_latents=True)
+    assert torch.allclose(one["latents"][0], a["latents"][200], atol=1e-5)
+
+
+def test_full_size_ddpm1000_b64_properties(engine):
+    """BASELINE configs[2] at full size (the bench workload): 64 clips x 1000 ancestral steps with in-kernel
+    Philox noise -- reproducible for a seed, seed-dependent, finite, and each half of the batch (what a
+    2-GPU shard would own) reproduces the full run's latents when given its global element offset."""
+    B = 64
+    g = torch.Generator().manual_seed(9)
+    l0, con, emo, sty = (torch.randn(B, d, generator=g) for d in (128, 256, 256, 256))
+    a = engine.denoise(l0, con, emo, sty, n_steps=1000, sampler="ddpm", seed=11)
+    b = engine.denoise(l0, con, emo, sty, n_steps=1000, sampler="ddpm", seed=11)
+    c = engine.denoise(l0, con, emo, sty, n_steps=1000, sampler="ddpm", seed=12)
+    assert torch.equal(a, b) and not torch.equal(a, c) and torch.isfinite(a).all()
+    poses, trans = engine.decode(a)
+    assert torch.isfinite(poses).all() and poses.shape == (B, 300, 55, 3)
+    assert poses.abs().max().item() <= 3.1416 + 1e-3          # axis-angle magnitude is an angle in [0, pi]
