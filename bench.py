@@ -39,6 +39,10 @@ FLOP_DENOISE_PER_CLIP_STEP = 19.219e6      # BASELINE.md section 3 (2*M*N*K of e
 FLOP_DECODE_PER_CLIP = 1.7595e9
 FLOP_AST_PER_CLIP = 783.08e9               # 3 branches x 261.03 GFLOP
 AUDIO_SAMPLES = 160000                     # 10 s at 16 kHz
+# dram__bytes_read.sum + dram__bytes_write.sum of one denoise_loop_kernel launch (ncu --set full,
+# profiles/r01_denoise_loop_full.txt): the 8.77 MB of repacked weights are read from HBM once per launch and
+# served from L2 for every later step; activations never leave shared memory (0 B written).
+DENOISE_LOOP_DRAM_BYTES = 8045312
 METRIC = "SMPL-X pose frames/sec over full DDPM sampling (10 s clip, batch 64)"
 
 
@@ -438,7 +442,7 @@ def run_ours(args, rank, world, local_rank):
                 "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "denoise_loop_kernel", "achieved": ach_tf, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": None,
+                     "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": DENOISE_LOOP_DRAM_BYTES,
                      "note": f"algorithmic 19.219 MFLOP x {B} clips x {N_STEPS} steps per launch; peak = {peak_kind} dense bf16 "
                              "(sustained); the kernel computes in fp32 FFMA and is dependency-latency bound at 5 rows/clip"},
         "cpu_baseline": {"value": cpu_value, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
