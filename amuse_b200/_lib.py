@@ -17,7 +17,7 @@ SYMBOLS = [
     "amuse_finalize_weights", "amuse_reserve", "amuse_denoise", "amuse_denoiser_eps", "amuse_decode",
     "amuse_rot6d_to_axis_angle", "amuse_diffusion_backward", "amuse_diffusion_backward_host",
     "amuse_ast_features", "amuse_schedule", "amuse_launch_count", "amuse_profile_arm", "amuse_profile_read",
-    "amuse_debug_tc_gemm", "amuse_debug_attn_profile", "amuse_fbank", "amuse_encode", "amuse_motion_to_feats",
+    "amuse_debug_tc_gemm", "amuse_debug_attn_profile", "amuse_debug_set_decode_plan", "amuse_fbank", "amuse_encode", "amuse_motion_to_feats",
 ]
 
 AMUSE_OK = 0
@@ -74,6 +74,7 @@ def load() -> C.CDLL:
     lib.amuse_profile_read.argtypes = [p, C.POINTER(i64), i]
     lib.amuse_fbank.argtypes = [p, i, i, p, f, f, p, p]
     lib.amuse_debug_attn_profile.argtypes = [p, i, p, i]
+    lib.amuse_debug_set_decode_plan.argtypes = [p, i, i]
     lib.amuse_encode.argtypes = [p, i, p, p, p, p]
     lib.amuse_motion_to_feats.argtypes = [p, i64, p, p, p, p]
     lib.amuse_debug_tc_gemm.argtypes = [p, i, i, i, i, p, p, i, p, p, p, p, p, i, p, p]

@@ -130,6 +130,11 @@ struct amuse_ctx {
   int prof_step = -1;
   int64_t launches = 0;
   int dec_chunk = 32;   // clips per decoder pass (keeps the working set inside the 126 MB L2)
+  // two decoder passes run concurrently on side streams: a 32-clip pass has 75 GEMM tiles, half the SMs
+  static constexpr int kMaxLanes = 4;
+  int dec_lanes = 2;
+  cudaStream_t side[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -785,12 +790,22 @@ int run_decode_tc(amuse_ctx* ctx, int B, const float* latents, float* feats6d, f
   const int chunk = ctx->dec_chunk;
   const size_t Mc = static_cast<size_t>(std::min(B, chunk)) * kFrames;
   const size_t n128 = Mc * 128;
-  for (int i = 0; i < 3; ++i) CU(ctx->tX[i].ensure(2 * n128));
-  CU(ctx->tSkip.ensure(2 * n128 * 4));
-  CU(ctx->tO.ensure(2 * n128));
-  CU(ctx->tH.ensure(2 * Mc * 512));
-  CU(ctx->dQKV.ensure(Mc * 384));
-  CU(ctx->dFeats.ensure(Mc * kFeats));
+  // lanes: passes in flight at once, each with its own workspace
+  const int n_pass = (B + chunk - 1) / chunk;
+  const int NL = std::max(1, std::min(std::min(ctx->dec_lanes, n_pass), static_cast<int>(amuse_ctx::kMaxLanes)));
+  for (int i = 0; i < 3; ++i) CU(ctx->tX[i].ensure(NL * 2 * n128));
+  CU(ctx->tSkip.ensure(NL * 2 * n128 * 4));
+  CU(ctx->tO.ensure(NL * 2 * n128));
+  CU(ctx->tH.ensure(NL * 2 * Mc * 512));
+  CU(ctx->dQKV.ensure(NL * Mc * 384));
+  CU(ctx->dFeats.ensure(NL * Mc * kFeats));
+  if (NL > 1 && !ctx->ev_fork) {
+    for (int i = 0; i < amuse_ctx::kMaxLanes; ++i) {
+      CU(cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  }
   CU(ctx->dCvec.ensure(static_cast<size_t>(9) * B * 128));
   if (!ctx->dZero.p) {
     CU(ctx->dZero.ensure(128));
@@ -801,16 +816,25 @@ int run_decode_tc(amuse_ctx* ctx, int B, const float* latents, float* feats6d, f
     float* lo;
   };
   auto planes = [&](DevBuf& b, size_t n, size_t idx = 0) { return P{b.p + idx * 2 * n, b.p + idx * 2 * n + n}; };
-  const P XA = planes(ctx->tX[0], n128), XB = planes(ctx->tX[1], n128), XC = planes(ctx->tX[2], n128);
-  const P O = planes(ctx->tO, n128), H = planes(ctx->tH, Mc * 512);
-  auto SK = [&](int i) { return planes(ctx->tSkip, n128, static_cast<size_t>(i)); };
 
-  CU(launch_cross_vectors(latents, W + d.wv_t, W + d.bv, W + d.wco_t, W + d.bco, ctx->dCvec.p, B, st));
+  cudaStream_t const caller = st;
+  CU(launch_cross_vectors(latents, W + d.wv_t, W + d.bv, W + d.wco_t, W + d.bco, ctx->dCvec.p, B, caller));
   ctx->launches++;
+  if (NL > 1) {   // fork: the side streams start after everything queued on the caller's stream so far
+    CU(cudaEventRecord(ctx->ev_fork, caller));
+    for (int i = 0; i < NL; ++i) CU(cudaStreamWaitEvent(ctx->side[i], ctx->ev_fork, 0));
+  }
 
-  for (int b0 = 0; b0 < B; b0 += chunk) {
+  int pass = 0;
+  for (int b0 = 0; b0 < B; b0 += chunk, ++pass) {
     const int nb = std::min(chunk, B - b0);
     const int M = nb * kFrames;
+    const size_t lane = static_cast<size_t>(pass % NL);
+    st = (NL > 1) ? ctx->side[lane] : caller;
+    const P XA = planes(ctx->tX[0], n128, lane), XB = planes(ctx->tX[1], n128, lane), XC = planes(ctx->tX[2], n128, lane);
+    const P O = planes(ctx->tO, n128, lane), H = planes(ctx->tH, Mc * 512, lane);
+    auto SK = [&](int i) { return planes(ctx->tSkip, n128, lane * 4 + static_cast<size_t>(i)); };
+    float* const qkv_ws = ctx->dQKV.p + lane * Mc * 384;
     // queries = zeros + pe[:300] (vae.py:221,253), as planes
     CU(launch_broadcast_rows(W + d.p_pe, XB.hi, nb, kFrames, st));
     CU(launch_broadcast_rows(W + d.p_pe + 500 * 128, XB.lo, nb, kFrames, st));
@@ -835,9 +859,9 @@ int run_decode_tc(amuse_ctx* ctx, int B, const float* latents, float* feats6d, f
       g.A_hi = cur.hi; g.A_lo = cur.lo; g.lda = 128;
       g.W_hi = W + L.p_qkv; g.W_lo = g.W_hi + 384 * 128; g.ldw = 128;
       g.M = M; g.N = 384; g.K = 128; g.bias = W + L.bqkv;
-      g.C = ctx->dQKV.p; g.ldc = 384; g.q_cols = 128; g.q_scale = 0.17677669529663687f;
+      g.C = qkv_ws; g.ldc = 384; g.q_cols = 128; g.q_scale = 0.17677669529663687f;
       CU(tc::gemm(tc::EPI_QKV, g, st));
-      CU(launch_self_attention_planes(ctx->dQKV.p, O.hi, O.lo, nb, kFrames, st));
+      CU(launch_self_attention_planes(qkv_ws, O.hi, O.lo, nb, kFrames, st));
       // y = norm2(norm1(x + out_proj(o)) + cross_vector)
       g = tc::GemmDesc{};
       g.A_hi = O.hi; g.A_lo = O.lo; g.lda = 128;
@@ -874,7 +898,7 @@ int run_decode_tc(amuse_ctx* ctx, int B, const float* latents, float* feats6d, f
       ctx->launches += 5;
       cur = out;
     }
-    float* feats = feats6d ? feats6d + static_cast<size_t>(b0) * kFrames * kFeats : ctx->dFeats.p;
+    float* feats = feats6d ? feats6d + static_cast<size_t>(b0) * kFrames * kFeats : ctx->dFeats.p + lane * Mc * kFeats;
     tc::GemmDesc g{};
     g.A_hi = cur.hi; g.A_lo = cur.lo; g.lda = 128;
     g.W_hi = W + d.p_final; g.W_lo = g.W_hi + kFeats * 128; g.ldw = 128;
@@ -886,6 +910,12 @@ int run_decode_tc(amuse_ctx* ctx, int B, const float* latents, float* feats6d, f
       CU(launch_rot6d(feats, kFeats, static_cast<long long>(M), poses + static_cast<size_t>(b0) * kFrames * 165,
                       trans ? trans + static_cast<size_t>(b0) * kFrames * 3 : nullptr, st));
       ctx->launches++;
+    }
+  }
+  if (NL > 1) {   // join: the caller's stream continues after every lane
+    for (int i = 0; i < NL; ++i) {
+      CU(cudaEventRecord(ctx->ev_join[i], ctx->side[i]));
+      CU(cudaStreamWaitEvent(caller, ctx->ev_join[i], 0));
     }
   }
   return AMUSE_OK;
@@ -1054,6 +1084,11 @@ void amuse_destroy(amuse_ctx* ctx) {
                     &ctx->tSkip, &ctx->tO, &ctx->tH, &ctx->mel_t, &ctx->enc.arena, &ctx->eFeat, &ctx->eEmb};
   for (DevBuf* b : bufs) b->release();
   ast::release(ctx->astw);
+  for (int i = 0; i < amuse_ctx::kMaxLanes; ++i) {
+    if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
+    if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->d_prof) cudaFree(ctx->d_prof);
   delete ctx;
 }
@@ -1334,6 +1369,13 @@ int amuse_fbank(amuse_ctx* ctx, int B, int n_samples, const float* wave, float n
   }
   CU(fb::launch(wave, B, n_samples, ctx->mel_t.p, norm_mean, norm_std, fbank, st));
   ctx->launches++;
+  return AMUSE_OK;
+}
+
+int amuse_debug_set_decode_plan(amuse_ctx* ctx, int clips_per_pass, int lanes) {
+  if (!ctx || clips_per_pass < 1 || lanes < 1 || lanes > amuse_ctx::kMaxLanes) return fail(ctx, AMUSE_E_INVALID, "bad argument");
+  ctx->dec_chunk = clips_per_pass;
+  ctx->dec_lanes = lanes;
   return AMUSE_OK;
 }
 
