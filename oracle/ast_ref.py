@@ -1,11 +1,15 @@
 """CPU restatement of the audio side of the path: ``process_single_seq`` and the three AST encoders.
 
-TEST INFRASTRUCTURE (see oracle/__init__.py).  PARITY UNPINNED: the encoders are timm-0.4.5
-``vit_deit_base_distilled_patch16_384`` models (``timm==0.4.5`` hard-asserted at
-models/audio/audio_main_new.py:52, pinned in amuse.yml:281) and timm is not installed in the
-build container, nor does the reference hold tests or golden vectors for them.  The maths below
-restates the published DeiT/ViT block as timm 0.4.5 implements it, anchored on the reference's own
-forward (models/audio/audio_main_new.py:174-204) and eval entry (models/audio/AST_EVP.py:84-90):
+TEST INFRASTRUCTURE (see oracle/__init__.py).  PARITY UNPINNED against the reference itself: the
+encoders are timm-0.4.5 ``vit_deit_base_distilled_patch16_384`` models (``timm==0.4.5`` hard-asserted
+at models/audio/audio_main_new.py:52, pinned in amuse.yml:281) and timm is not installed in the
+build container, nor does the reference hold tests or golden vectors for them.  What IS checked: the
+same weights through the image's HuggingFace ``transformers.ASTModel`` -- an independent implementation
+of the same published AST/DeiT encoder -- agree with this restatement to 7e-7 on |feat| = 3.3
+(tests/test_oracle.py::test_ast_restatement_matches_hf_transformers; runs on the GPU box too).
+The maths below restates the published DeiT/ViT block as timm 0.4.5 implements it, anchored on the
+reference's own forward (models/audio/audio_main_new.py:174-204) and eval entry
+(models/audio/AST_EVP.py:84-90):
 
     x [B,1024,128] -> unsqueeze(1).transpose(2,3) -> Conv2d(1,768,k=16,s=10) -> [B,768,12,101]
       -> flatten(2).transpose(1,2) [B,1212,768]; prepend cls, dist; + pos_embed [1,1214,768]

@@ -127,3 +127,59 @@ def test_encode_golden(golden_dir, sds):
     mu64, lv64 = R.vae_encode(v64, R.motion_to_feats(poses.double(), trans.double()))
     assert np.abs(mu64.numpy() - g["mu_f64"]).max() < 1e-10
     assert np.abs(lv64.exp().pow(0.5).numpy() - g["std_f64"]).max() < 1e-10
+
+
+def _timm_to_hf(sd, prefix):
+    """timm-0.4.5 DeiT key names (oracle/weights.py) -> HuggingFace ``ASTModel`` key names."""
+    v = f"{prefix}.v"
+    out = {"embeddings.cls_token": sd[f"{v}.cls_token"], "embeddings.distillation_token": sd[f"{v}.dist_token"],
+           "embeddings.position_embeddings": sd[f"{v}.pos_embed"],
+           "embeddings.patch_embeddings.projection.weight": sd[f"{v}.patch_embed.proj.weight"],
+           "embeddings.patch_embeddings.projection.bias": sd[f"{v}.patch_embed.proj.bias"],
+           "layernorm.weight": sd[f"{v}.norm.weight"], "layernorm.bias": sd[f"{v}.norm.bias"]}
+    i = 0
+    while f"{v}.blocks.{i}.norm1.weight" in sd:
+        b, h = f"{v}.blocks.{i}", f"encoder.layer.{i}"
+        D = sd[f"{b}.attn.proj.weight"].shape[0]
+        for j, nm in enumerate(("query", "key", "value")):        # timm packs q|k|v along the output axis
+            out[f"{h}.attention.attention.{nm}.weight"] = sd[f"{b}.attn.qkv.weight"][j * D:(j + 1) * D]
+            out[f"{h}.attention.attention.{nm}.bias"] = sd[f"{b}.attn.qkv.bias"][j * D:(j + 1) * D]
+        for wb in ("weight", "bias"):
+            out[f"{h}.attention.output.dense.{wb}"] = sd[f"{b}.attn.proj.{wb}"]
+            out[f"{h}.layernorm_before.{wb}"] = sd[f"{b}.norm1.{wb}"]
+            out[f"{h}.layernorm_after.{wb}"] = sd[f"{b}.norm2.{wb}"]
+            out[f"{h}.intermediate.dense.{wb}"] = sd[f"{b}.mlp.fc1.{wb}"]
+            out[f"{h}.output.dense.{wb}"] = sd[f"{b}.mlp.fc2.{wb}"]
+        i += 1
+    return out, i
+
+
+def test_ast_restatement_matches_hf_transformers():
+    """Independent pin of the AST restatement (oracle/ast_ref.py).  timm 0.4.5 (what the reference
+    asserts, audio_main_new.py:52) is not installable, but the image's ``transformers`` ships its own
+    implementation of the same published AST/DeiT encoder (``ASTModel``: 16x16 patches, stride 10,
+    cls + distillation tokens, pre-LN blocks).  Same weights through both must agree; the reference's
+    frame-based head (audio_main_new.py:196-204: mean of tokens 2:, LayerNorm, Linear) is applied to
+    HF's ``last_hidden_state`` here."""
+    tr = pytest.importorskip("transformers")
+    from oracle import ast_ref as A
+    sd = W.ast_state_dict(depth=2)
+    g = torch.Generator().manual_seed(7)
+    fb = torch.randn(2, 1024, 128, generator=g)
+    for prefix in ("con_enc", "emo_enc"):
+        hf_sd, depth = _timm_to_hf(sd, prefix)
+        cfg = tr.ASTConfig(num_hidden_layers=depth, layer_norm_eps=1e-6, hidden_dropout_prob=0.0,
+                           attention_probs_dropout_prob=0.0)
+        model = tr.ASTModel(cfg).eval()
+        missing = model.load_state_dict(hf_sd, strict=True)
+        assert not missing.missing_keys and not missing.unexpected_keys
+        with torch.no_grad():
+            tokens = model(input_values=fb).last_hidden_state                       # after the final LayerNorm
+            feat = tokens[:, 2:].mean(dim=1)
+            feat = torch.nn.functional.layer_norm(feat, (768,), sd[f"{prefix}.feature_head.0.weight"],
+                                                  sd[f"{prefix}.feature_head.0.bias"], 1e-5)
+            want = torch.nn.functional.linear(feat, sd[f"{prefix}.feature_head.1.weight"],
+                                              sd[f"{prefix}.feature_head.1.bias"])
+            got = A.ast_branch(sd, prefix, fb)
+        assert got.shape == (2, 256)
+        assert float((got - want).abs().max()) < 2e-5 * max(1.0, float(want.abs().max()))
