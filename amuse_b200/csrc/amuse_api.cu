@@ -112,6 +112,9 @@ struct amuse_ctx {
   int device = 0;
   std::string err;
   std::unordered_map<std::string, HostTensor> raw;
+  // which weight groups changed since the last finalize: a re-finalize repacks only those (the
+  // training-time caller refreshes the denoiser every iteration while the VAE stays frozen, ldm.py:118-153)
+  bool dirty_den = false, dirty_vae = false;
   std::vector<float> alphas_cumprod;   // 1000 entries; default computed at create
   DenW den;
   DecW dec;
@@ -1117,6 +1120,7 @@ int amuse_load_weights(amuse_ctx* ctx, const char* name, const void* data, const
   if (key.compare(0, 9, "denoiser.") != 0 && key.compare(0, 4, "vae.") != 0)
     return fail(ctx, AMUSE_E_INVALID, "unknown weight namespace in '%s'", name);
   if (key == "denoiser.mem_pos.pe") return AMUSE_OK;   // never read by the reference's forward (denoiser.py:174-188)
+  (key[0] == 'd' ? ctx->dirty_den : ctx->dirty_vae) = true;
   HostTensor t;
   t.shape.assign(shape, shape + ndim);
   t.data.resize(static_cast<size_t>(n));
@@ -1131,17 +1135,22 @@ int amuse_finalize_weights(amuse_ctx* ctx, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   bool any = false;
   if (find(ctx, "denoiser.encoder.norm.weight")) {   // (a bare "denoiser.time_proj.freqs" table does not count)
-    if (int rc = pack_denoiser(ctx, st)) return rc;
+    if (ctx->dirty_den || !ctx->den.ready)
+      if (int rc = pack_denoiser(ctx, st)) return rc;
+    ctx->dirty_den = false;
     any = true;
   }
   if (find(ctx, "vae.decoder.norm.weight")) {
-    if (int rc = pack_decoder(ctx, st)) return rc;
+    if (ctx->dirty_vae || !ctx->dec.ready)
+      if (int rc = pack_decoder(ctx, st)) return rc;
     any = true;
   }
   if (find(ctx, "vae.encoder.norm.weight")) {   // optional: only the edit path (MotionPrior.encode) needs it
-    if (int rc = pack_encoder(ctx, st)) return rc;
+    if (ctx->dirty_vae || !ctx->enc.ready)
+      if (int rc = pack_encoder(ctx, st)) return rc;
     any = true;
   }
+  ctx->dirty_vae = false;
   if (ast::staged(ctx->astw)) {
     int rc = ast::finalize(ctx->astw, st);
     if (rc) return fail(ctx, rc, "ast finalize: %s", ast::last_error(ctx->astw));
