@@ -127,6 +127,7 @@ struct amuse_ctx {
   DevBuf tX[3], tSkip, tO, tH;   // tcgen05 decoder path: activation planes (hi | lo halves)
   DevBuf eFeat, eEmb;            // encoder: packed feature planes [rows][352] x 2, embedded frames [rows][128]
   bool dec_use_tc = true;        // decoder GEMMs on tcgen05 (3xTF32); false = fp32 FFMA kernels
+  int prune_last = 1;            // denoise loop: last layer for token 0 only (AMUSE_PRUNE_LAST=0 disables; tuning hook)
   DevBuf h2d;   // staging for the *_host entry point
   DevBuf mel_t; // [257][128] mel filterbank weights (K-major)
   long long* d_prof = nullptr;
@@ -668,6 +669,7 @@ int run_denoise(amuse_ctx* ctx, int B, Schedule& sc, int clip, const float* late
   p.clip = clip;
   p.seed = seed;
   p.seed_elem_base = elem_base;
+  p.prune_last = ctx->prune_last;
   CU(dn::launch(p, st));
   ctx->launches++;
   ctx->prof_step = -1;
@@ -1068,6 +1070,7 @@ int amuse_create(amuse_ctx** out, int device_ordinal) {
   c->device = device_ordinal;
   default_alphas(c->alphas_cumprod);
   if (const char* e = getenv("AMUSE_DECODE_FFMA")) c->dec_use_tc = !(e[0] == '1');   // A/B switch for measurements
+  if (const char* e = getenv("AMUSE_PRUNE_LAST")) c->prune_last = (e[0] != '0');
   if (cudaMalloc(&c->d_prof, 128 * sizeof(long long)) != cudaSuccess) {
     delete c;
     return AMUSE_E_CUDA;

@@ -132,20 +132,21 @@ __device__ __forceinline__ void wp_release(const Smem& s, WPipe& w, int tid) {
 // unrolled: with a runtime trip count (or unroll 2) the loads are not hoisted far enough ahead of
 // the FFMA2s and every GEMM stage got 15-25% slower (measured), which outweighs the extra
 // instruction-cache pressure of the larger body.
-template <int NCOL, int TC, int ITERS>
-__device__ __forceinline__ void gemm5(const float* __restrict__ a0, int lda, const float* __restrict__ w,
-                                      float (&acc)[5][TC]) {
+// NR = rows per warp: 5 (one clip's tokens) everywhere, except in the pruned last layer (1 or 2 rows).
+template <int NR, int NCOL, int TC, int ITERS>
+__device__ __forceinline__ void gemm_rows(const float* __restrict__ a0, int lda, const float* __restrict__ w,
+                                          float (&acc)[NR][TC]) {
   static_assert(NCOL == 32 * TC, "lane owns tile positions lane + 32*j");
-  float2 acc2[5][TC];
+  float2 acc2[NR][TC];
 #pragma unroll
-  for (int i = 0; i < 5; ++i)
+  for (int i = 0; i < NR; ++i)
 #pragma unroll
     for (int j = 0; j < TC; ++j) acc2[i][j] = make_float2(0.f, 0.f);
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
-    float4 a[5];
+    float4 a[NR];
 #pragma unroll
-    for (int i = 0; i < 5; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + i * lda + it * 4);
+    for (int i = 0; i < NR; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + i * lda + it * 4);
 #pragma unroll
     for (int kp = 0; kp < 2; ++kp) {
       float2 wv[TC];
@@ -153,7 +154,7 @@ __device__ __forceinline__ void gemm5(const float* __restrict__ a0, int lda, con
 #pragma unroll
       for (int j = 0; j < TC; ++j) wv[j] = *reinterpret_cast<const float2*>(wr + 64 * j);
 #pragma unroll
-      for (int i = 0; i < 5; ++i) {
+      for (int i = 0; i < NR; ++i) {
         const float2 av = (kp == 0) ? make_float2(a[i].x, a[i].y) : make_float2(a[i].z, a[i].w);
 #pragma unroll
         for (int j = 0; j < TC; ++j) acc2[i][j] = __ffma2_rn(av, wv[j], acc2[i][j]);
@@ -161,9 +162,14 @@ __device__ __forceinline__ void gemm5(const float* __restrict__ a0, int lda, con
     }
   }
 #pragma unroll
-  for (int i = 0; i < 5; ++i)
+  for (int i = 0; i < NR; ++i)
 #pragma unroll
     for (int j = 0; j < TC; ++j) acc[i][j] = acc2[i][j].x + acc2[i][j].y;
+}
+template <int NCOL, int TC, int ITERS>
+__device__ __forceinline__ void gemm5(const float* __restrict__ a0, int lda, const float* __restrict__ w,
+                                      float (&acc)[5][TC]) {
+  gemm_rows<5, NCOL, TC, ITERS>(a0, lda, w, acc);
 }
 
 // K-split reduction through shared memory.  Every warp parks its partial tile in
@@ -198,6 +204,17 @@ __device__ __forceinline__ void park4(float* RED, int rb, int ks, int lane, cons
     v.lo = make_float2(acc[i][0], acc[i][1]);
     v.hi = make_float2(acc[i][2], acc[i][3]);
     st_row4(dst + i * 128, lane, v);
+  }
+}
+// pruned last layer: NR rows per warp, all 8 warps split K; RED[ks][NR][128]
+template <int NR>
+__device__ __forceinline__ void park_rows(float* RED, int ks, int lane, const float (&acc)[NR][4]) {
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    Row4 v;
+    v.lo = make_float2(acc[i][0], acc[i][1]);
+    v.hi = make_float2(acc[i][2], acc[i][3]);
+    st_row4(RED + (ks * NR + i) * 128, lane, v);
   }
 }
 template <int RT, int KS>
@@ -249,9 +266,13 @@ __device__ __forceinline__ Row4 add_peers(const float* Ps, int row, int lane, Ro
 __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
 // LayerNorm of up to two 128-wide rows held 4 values per lane; the two chains are interleaved.
+// One butterfly instead of two: sum and sum of squares of d = x - c are reduced together, with the
+// shift c = first element of the row (one extra shuffle), so that var = E[d^2] - E[d]^2 does not
+// cancel (|E[d]| is of the order of the row's standard deviation, not of its mean).
 __device__ __forceinline__ void layernorm2(Row4 (&v)[2], const float* lnp, int lane) {
   const Row4 g = ld_row4(lnp, lane), be = ld_row4(lnp + 128, lane);
   float s1[2], s2[2];
+#ifdef AMUSE_LN_TWOPASS   // A/B switch: the textbook two-butterfly form
 #pragma unroll
   for (int i = 0; i < 2; ++i) s1[i] = (v[i].lo.x + v[i].lo.y) + (v[i].hi.x + v[i].hi.y);
 #pragma unroll
@@ -277,6 +298,33 @@ __device__ __forceinline__ void layernorm2(Row4 (&v)[2], const float* lnp, int l
     v[i].lo = make_float2(v[i].lo.x * rstd * g.lo.x + be.lo.x, v[i].lo.y * rstd * g.lo.y + be.lo.y);
     v[i].hi = make_float2(v[i].hi.x * rstd * g.hi.x + be.hi.x, v[i].hi.y * rstd * g.hi.y + be.hi.y);
   }
+  return;
+#endif
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float c = __shfl_sync(0xffffffffu, v[i].lo.x, 0);
+    v[i].lo.x -= c;
+    v[i].lo.y -= c;
+    v[i].hi.x -= c;
+    v[i].hi.y -= c;
+    s1[i] = (v[i].lo.x + v[i].lo.y) + (v[i].hi.x + v[i].hi.y);
+    s2[i] = (v[i].lo.x * v[i].lo.x + v[i].lo.y * v[i].lo.y) + (v[i].hi.x * v[i].hi.x + v[i].hi.y * v[i].hi.y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
+      s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
+    }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float mean = s1[i] * (1.0f / 128.0f);
+    const float var = fmaxf(fmaf(-mean, mean, s2[i] * (1.0f / 128.0f)), 0.f);
+    const float rstd = rsqrtf(var + kLnEps);
+    v[i].lo = make_float2((v[i].lo.x - mean) * rstd * g.lo.x + be.lo.x, (v[i].lo.y - mean) * rstd * g.lo.y + be.lo.y);
+    v[i].hi = make_float2((v[i].hi.x - mean) * rstd * g.hi.x + be.hi.x, (v[i].hi.y - mean) * rstd * g.hi.y + be.hi.y);
+  }
 }
 
 __device__ __forceinline__ void copy_params(float* dst, const float* src, int n, int tid) {
@@ -293,7 +341,11 @@ __device__ __forceinline__ void copy_params(float* dst, const float* src, int n,
 
 // ================================================================= the kernel
 // RB = row blocks of 5 rows: 1 (one clip per cluster) or 2 (two clips).  8 warps = RB x KS.
-template <int RB>
+// PRUNE: after the last layer only token 0 of every clip is read (encoder.norm -> eps, denoiser.py:188),
+// so its out_proj / FFN1 / FFN2 are evaluated for RB rows instead of 5*RB: all 8 warps split K, every
+// weight tile is read from shared memory once, and the exchanges carry RB rows.  K and V of the last
+// layer still need all tokens, so the skip-linear, QKV and attention stages are unchanged.
+template <int RB, bool PRUNE>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     denoise_loop_kernel(const Params p) {
   constexpr int KS = 8 / RB;      // K-split factor of every GEMM
@@ -374,6 +426,18 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   float noise_next = 0.f;
   if (!use_rng && owns_elem) noise_next = __ldg(p.step_noise + static_cast<size_t>(s_base) * 128 + tid);
 
+  // attention roles (see the attention stage): lane -> (row slot, key j, half c of the head dimension)
+  const int at_slot = (lane < 30) ? lane / 10 : 0;
+  const int at_l = lane - (lane / 10) * 10;                    // position inside the slot: j * 2 + c
+  const bool at_live = (lane < 30) && (warp * 3 + at_slot < R);
+  const int at_row = at_live ? warp * 3 + at_slot : 0;         // my query row (compact: clip * T + token)
+  const int at_cb = (at_row / T) * T;                          // first row of that clip
+  const int at_c = at_l & 1;
+  const bool at_key = at_live && (at_l >> 1) < T;              // my key exists
+  const int at_j = at_key ? (at_l >> 1) : 0;
+  const int at_src = at_slot * 10;                             // lane holding (j = 0, c = 0) of my slot
+  const bool at_pv = at_live && at_l < 8;
+
   // K-split partial -> st.async exchange -> sum + bias [+ residual] [+ LayerNorm] -> Xs [, skip stack].
   // A lambda so that the three users (skip fusion, out_proj, FFN2) share one source form.
   auto exchange_epilogue = [&](const float* bias, const float* resid, const float* lnp, float* dst2, int prof_slot,
@@ -407,6 +471,27 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         st_row4(Xs + row1 * 128, lane, v[1]);
         if (dst2) st_row4(dst2 + row1 * 128, lane, v[1]);
       }
+    }
+    ++xe;
+    __syncthreads();
+  };
+
+  // Pruned-row variant (last layer): warp i < RB owns token 0 of clip i, i.e. activation row i*T.  A
+  // cluster with fewer clips than RB still sends RB rows (the spare row is finite filler that nobody
+  // reads), so the byte count every CTA arms its mbarrier with is a compile-time constant.
+  auto exchange_epilogue_pruned = [&](const float* bias, const float* lnp, int prof_slot, bool do_prof) {
+    if (warp < RB) {
+      const int arow = warp * T;
+      Row4 v[2];
+      v[0] = gather4<RB, 8>(RED, warp, lane);
+      send_row(s, xe, rank, arow, lane, v[0]);
+      v[0] = add4(add4(v[0], ld_row4(bias, lane)), ld_row4(Xs + arow * 128, lane));
+      exchange_wait(s, xe);
+      if (prof_slot >= 0 && do_prof && tid == 0) p.prof[prof_slot] = clock64();
+      v[0] = add_peers(s.Ps(xe & 1), arow, lane, v[0]);
+      v[1] = v[0];
+      layernorm2(v, lnp, lane);
+      st_row4(Xs + arow * 128, lane, v[0]);
     }
     ++xe;
     __syncthreads();
@@ -506,52 +591,106 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       }
       AMUSE_PROF(2 + layer * 10 + 1);
 
-      // =============== attention: T x T per clip for my head, one warp per clip
-      if (warp < S) {
-        const float* base = QKVs + warp * T * kQkvLd;
-        const int i = (lane < 25) ? lane / 5 : 0, j = lane % 5;
-        const bool valid = (lane < 25) && (i < T) && (j < T);
-        const int ic = valid ? i : 0, jc = valid ? j : 0;
-        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
-        const float4* qv = reinterpret_cast<const float4*>(base + ic * kQkvLd);
-        const float4* kv = reinterpret_cast<const float4*>(base + jc * kQkvLd + 32);
+      // =============== attention of my head.  A lone warp runs at ~6 cycles per dependent instruction
+      // here (measured), so the work is laid out for the shortest per-warp instruction chain: 3 query rows
+      // per warp (warps 0..3), 10 lanes per row = 5 keys x 2 halves of the head dimension.
+      if (warp < 4) {
+        const float4* qv = reinterpret_cast<const float4*>(QKVs + at_row * kQkvLd + 16 * at_c);
+        const float4* kv = reinterpret_cast<const float4*>(QKVs + (at_cb + at_j) * kQkvLd + 32 + 16 * at_c);
+        float p0, p1, p2, p3;
+        {
+          const float4 a = qv[0], b = kv[0];
+          p0 = a.x * b.x;
+          p1 = a.y * b.y;
+          p2 = a.z * b.z;
+          p3 = a.w * b.w;
+        }
 #pragma unroll
-        for (int c = 0; c < 8; c += 2) {
-          const float4 a = qv[c], b = kv[c], a2 = qv[c + 1], b2 = kv[c + 1];
+        for (int c = 1; c < 4; ++c) {
+          const float4 a = qv[c], b = kv[c];
           p0 = fmaf(a.x, b.x, p0);
           p1 = fmaf(a.y, b.y, p1);
           p2 = fmaf(a.z, b.z, p2);
           p3 = fmaf(a.w, b.w, p3);
-          p0 = fmaf(a2.x, b2.x, p0);
-          p1 = fmaf(a2.y, b2.y, p1);
-          p2 = fmaf(a2.z, b2.z, p2);
-          p3 = fmaf(a2.w, b2.w, p3);
         }
-        const float sc = valid ? ((p0 + p1) + (p2 + p3)) : -INFINITY;
+        float sc = (p0 + p1) + (p2 + p3);
+        sc += __shfl_xor_sync(0xffffffffu, sc, 1);          // the two halves of the head dimension
         float sj[5];
 #pragma unroll
-        for (int jj = 0; jj < 5; ++jj) sj[jj] = __shfl_sync(0xffffffffu, sc, i * 5 + jj);
-        const float m = fmaxf(fmaxf(fmaxf(sj[0], sj[1]), fmaxf(sj[2], sj[3])), sj[4]);
-        const float e = valid ? expf(sc - m) : 0.f;
+        for (int jj = 0; jj < 5; ++jj) sj[jj] = __shfl_sync(0xffffffffu, sc, at_src + 2 * jj);
+        float m = sj[0];
+#pragma unroll
+        for (int jj = 1; jj < 5; ++jj) m = (jj < T) ? fmaxf(m, sj[jj]) : m;
+        const float e = at_key ? expf(sc - m) : 0.f;
         float ej[5];
 #pragma unroll
-        for (int jj = 0; jj < 5; ++jj) ej[jj] = __shfl_sync(0xffffffffu, e, i * 5 + jj);
-        const float sum = (ej[0] + ej[1]) + (ej[2] + ej[3]) + ej[4];
-        const float pr = valid ? e / sum : 0.f;
-        float vj[5];
+        for (int jj = 0; jj < 5; ++jj) ej[jj] = __shfl_sync(0xffffffffu, e, at_src + 2 * jj);
+        const float sum = ((ej[0] + ej[1]) + (ej[2] + ej[3])) + ej[4];
+        if (at_pv) {   // 8 lanes per row: 4 head dimensions each
+          const float* vb = QKVs + at_cb * kQkvLd + 64 + 4 * at_l;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int jj = 0; jj < 5; ++jj) vj[jj] = (jj < T) ? base[jj * kQkvLd + 64 + lane] : 0.f;
-#pragma unroll
-        for (int ii = 0; ii < 5; ++ii) {
-          float o = 0.f;
-#pragma unroll
-          for (int jj = 0; jj < 5; ++jj) o = fmaf(__shfl_sync(0xffffffffu, pr, ii * 5 + jj), vj[jj], o);
-          if (ii < T) Oh[(warp * T + ii) * kOhLd + lane] = o;
+          for (int jj = 0; jj < 5; ++jj)
+            if (jj < T) {
+              const float4 v4 = *reinterpret_cast<const float4*>(vb + jj * kQkvLd);
+              acc.x = fmaf(ej[jj], v4.x, acc.x);
+              acc.y = fmaf(ej[jj], v4.y, acc.y);
+              acc.z = fmaf(ej[jj], v4.z, acc.z);
+              acc.w = fmaf(ej[jj], v4.w, acc.w);
+            }
+          const float inv = __frcp_rn(sum);
+          *reinterpret_cast<float4*>(Oh + at_row * kOhLd + 4 * at_l) =
+              make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
         }
       }
       __syncthreads();
       AMUSE_PROF(2 + layer * 10 + 2);
 
+      if (PRUNE && layer == kLayers - 1) {
+        // =============== last layer, token 0 of every clip only (see PRUNE above)
+        {   // out_proj
+          const float* wt = wp_acquire(s, wp);
+          exchange_arm<RB>(s, xe, tid);
+          copy_params(par_tail, wt + 32 * 128, kTileTail, tid);
+          float acc[RB][4];
+          gemm_rows<RB, 128, 4, 1>(Oh + warp * 4, T * kOhLd, wt + (warp * 2) * 256 + lane * 2, acc);
+          park_rows<RB>(RED, warp, lane, acc);
+          __syncthreads();
+          wp_release(s, wp, tid);
+          exchange_epilogue_pruned(par_tail, par_tail + 128, 2 + layer * 10 + 3, do_prof);
+        }
+        AMUSE_PROF(2 + layer * 10 + 4);
+        {   // FFN1 + erf-GELU
+          const float* wt = wp_acquire(s, wp);
+          copy_params(par_tail, wt + 128 * 128, 128, tid);
+          float acc[RB][4];
+          gemm_rows<RB, 128, 4, 4>(Xs + warp * 16, T * 128, wt + (warp * 8) * 256 + lane * 2, acc);
+          park_rows<RB>(RED, warp, lane, acc);
+          __syncthreads();
+          wp_release(s, wp, tid);
+          if (warp < RB) {
+            Row4 v = add4(gather4<RB, 8>(RED, warp, lane), ld_row4(par_tail, lane));
+            v.lo = make_float2(gelu_erf(v.lo.x), gelu_erf(v.lo.y));
+            v.hi = make_float2(gelu_erf(v.hi.x), gelu_erf(v.hi.y));
+            st_row4(Hs + (warp * T) * 128, lane, v);
+          }
+          __syncthreads();
+        }
+        AMUSE_PROF(2 + layer * 10 + 5);
+        {   // FFN2
+          const float* wt = wp_acquire(s, wp);
+          exchange_arm<RB>(s, xe, tid);
+          copy_params(par_tail, wt + 128 * 128, kTileTail, tid);
+          float acc[RB][4];
+          gemm_rows<RB, 128, 4, 4>(Hs + warp * 16, T * 128, wt + (warp * 8) * 256 + lane * 2, acc);
+          park_rows<RB>(RED, warp, lane, acc);
+          __syncthreads();
+          wp_release(s, wp, tid);
+          exchange_epilogue_pruned(par_tail, par_tail + 128, 2 + layer * 10 + 6, do_prof);
+        }
+        AMUSE_PROF(2 + layer * 10 + 7);
+        continue;
+      }
       // =============== out_proj, K-split by head -> st.async partial exchange -> sum + LN1
       {
         const float* wt = wp_acquire(s, wp);
@@ -642,22 +781,21 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
 size_t smem_bytes() { return static_cast<size_t>(kSmemFloats) * sizeof(float); }
 
 cudaError_t launch(const Params& p, cudaStream_t stream) {
+  using Kernel = void (*)(const Params);
+  static const Kernel kernels[2][2] = {{denoise_loop_kernel<1, false>, denoise_loop_kernel<1, true>},
+                                       {denoise_loop_kernel<2, false>, denoise_loop_kernel<2, true>}};
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(denoise_loop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem_bytes()));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(denoise_loop_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem_bytes()));
-    if (e != cudaSuccess) return e;
+    for (int i = 0; i < 4; ++i) {
+      cudaError_t e = cudaFuncSetAttribute(kernels[i >> 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem_bytes()));
+      if (e != cudaSuccess) return e;
+    }
     configured = true;
   }
   if (p.S < 1 || p.S > kSMax) return cudaErrorInvalidValue;
   const int n_clusters = (p.B + p.S - 1) / p.S;
-  if (p.S == 1)
-    denoise_loop_kernel<1><<<dim3(n_clusters * kCluster), dim3(kThreads), smem_bytes(), stream>>>(p);
-  else
-    denoise_loop_kernel<2><<<dim3(n_clusters * kCluster), dim3(kThreads), smem_bytes(), stream>>>(p);
+  kernels[p.S - 1][p.prune_last ? 1 : 0]<<<dim3(n_clusters * kCluster), dim3(kThreads), smem_bytes(), stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -69,6 +69,7 @@ struct Params {
   unsigned long long seed;   // Philox seed when step_noise == nullptr and sigma > 0
   unsigned long long seed_elem_base;   // global index of this launch's first latent element (multi-GPU shards)
   int prof_step;
+  int prune_last;            // last layer evaluated for token 0 only (same result; see denoise_loop.cu PRUNE)
 };
 
 size_t smem_bytes();
