@@ -90,9 +90,11 @@ struct WPipe {
   uint32_t total;      // n_steps * 40
 };
 
+__constant__ int2 c_tile_tab[kTilesPerStep];   // (offset, count) of tile i -- tile_info() evaluated once on the host
+
 __device__ __forceinline__ void wp_issue(const Smem& s, const WPipe& w, uint32_t n) {
-  int off, cnt;
-  tile_info(static_cast<int>(n % kTilesPerStep), off, cnt);
+  const int2 tab = c_tile_tab[n % kTilesPerStep];
+  const int off = tab.x, cnt = tab.y;
   uint64_t* bar = s.wbar(n & 1);
   mbar_arrive_expect_tx(bar, static_cast<uint32_t>(cnt) * 4u);
   bulk_g2s(s.wbuf(n & 1), w.blob + off, static_cast<uint32_t>(cnt) * 4u, bar);
@@ -102,11 +104,10 @@ __device__ __forceinline__ const float* wp_acquire(const Smem& s, const WPipe& w
   return s.wbuf(w.g & 1);
 }
 // Call after a __syncthreads() that follows the last read of tile g: hands the buffer back
-// to the TMA engine for tile g+2.  Issued by one lane of warp 7 -- the warp with the least
-// epilogue work -- so that the ~0.5k-cycle issue latency stays off the critical path (measured:
-// with thread 0 issuing, warp 0's epilogue was 700 cycles late in every stage).  No proxy fence:
-// the buffer was only READ by this CTA and every reader has passed the barrier.
-constexpr int kIssuerTid = 7 * 32;
+// to the TMA engine for tile g+2.  Issued by one lane of warp 9, which has no GEMM role (measured
+// earlier: with thread 0 issuing, warp 0's epilogue was 700 cycles late in every stage).  No proxy
+// fence: the buffer was only READ by this CTA and every reader has passed the barrier.
+constexpr int kIssuerTid = 9 * 32;
 __device__ __forceinline__ void wp_release(const Smem& s, WPipe& w, int tid) {
   if (tid == kIssuerTid && w.g + 2 < w.total) wp_issue(s, w, w.g + 2);
   ++w.g;
@@ -265,66 +266,29 @@ __device__ __forceinline__ Row4 add_peers(const float* Ps, int row, int lane, Ro
 }
 __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
-// LayerNorm of up to two 128-wide rows held 4 values per lane; the two chains are interleaved.
+// LayerNorm of one 128-wide row held 4 values per lane (nn.LayerNorm: biased variance, eps 1e-5).
 // One butterfly instead of two: sum and sum of squares of d = x - c are reduced together, with the
 // shift c = first element of the row (one extra shuffle), so that var = E[d^2] - E[d]^2 does not
 // cancel (|E[d]| is of the order of the row's standard deviation, not of its mean).
-__device__ __forceinline__ void layernorm2(Row4 (&v)[2], const float* lnp, int lane) {
+__device__ __forceinline__ void layernorm1(Row4& v, const float* lnp, int lane) {
   const Row4 g = ld_row4(lnp, lane), be = ld_row4(lnp + 128, lane);
-  float s1[2], s2[2];
-#ifdef AMUSE_LN_TWOPASS   // A/B switch: the textbook two-butterfly form
+  const float c = __shfl_sync(0xffffffffu, v.lo.x, 0);
+  v.lo.x -= c;
+  v.lo.y -= c;
+  v.hi.x -= c;
+  v.hi.y -= c;
+  float s1 = (v.lo.x + v.lo.y) + (v.hi.x + v.hi.y);
+  float s2 = (v.lo.x * v.lo.x + v.lo.y * v.lo.y) + (v.hi.x * v.hi.x + v.hi.y * v.hi.y);
 #pragma unroll
-  for (int i = 0; i < 2; ++i) s1[i] = (v[i].lo.x + v[i].lo.y) + (v[i].hi.x + v[i].hi.y);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-    for (int i = 0; i < 2; ++i) s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float mean = s1[i] * (1.0f / 128.0f);
-    v[i].lo.x -= mean;
-    v[i].lo.y -= mean;
-    v[i].hi.x -= mean;
-    v[i].hi.y -= mean;
-    s2[i] = (v[i].lo.x * v[i].lo.x + v[i].lo.y * v[i].lo.y) + (v[i].hi.x * v[i].hi.x + v[i].hi.y * v[i].hi.y);
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-    for (int i = 0; i < 2; ++i) s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float rstd = rsqrtf(s2[i] * (1.0f / 128.0f) + kLnEps);
-    v[i].lo = make_float2(v[i].lo.x * rstd * g.lo.x + be.lo.x, v[i].lo.y * rstd * g.lo.y + be.lo.y);
-    v[i].hi = make_float2(v[i].hi.x * rstd * g.hi.x + be.hi.x, v[i].hi.y * rstd * g.hi.y + be.hi.y);
-  }
-  return;
-#endif
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float c = __shfl_sync(0xffffffffu, v[i].lo.x, 0);
-    v[i].lo.x -= c;
-    v[i].lo.y -= c;
-    v[i].hi.x -= c;
-    v[i].hi.y -= c;
-    s1[i] = (v[i].lo.x + v[i].lo.y) + (v[i].hi.x + v[i].hi.y);
-    s2[i] = (v[i].lo.x * v[i].lo.x + v[i].lo.y * v[i].lo.y) + (v[i].hi.x * v[i].hi.x + v[i].hi.y * v[i].hi.y);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
-      s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
-    }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float mean = s1[i] * (1.0f / 128.0f);
-    const float var = fmaxf(fmaf(-mean, mean, s2[i] * (1.0f / 128.0f)), 0.f);
-    const float rstd = rsqrtf(var + kLnEps);
-    v[i].lo = make_float2((v[i].lo.x - mean) * rstd * g.lo.x + be.lo.x, (v[i].lo.y - mean) * rstd * g.lo.y + be.lo.y);
-    v[i].hi = make_float2((v[i].hi.x - mean) * rstd * g.hi.x + be.hi.x, (v[i].hi.y - mean) * rstd * g.hi.y + be.hi.y);
-  }
+  const float mean = s1 * (1.0f / 128.0f);
+  const float var = fmaxf(fmaf(-mean, mean, s2 * (1.0f / 128.0f)), 0.f);
+  const float rstd = rsqrtf(var + kLnEps);
+  v.lo = make_float2((v.lo.x - mean) * rstd * g.lo.x + be.lo.x, (v.lo.y - mean) * rstd * g.lo.y + be.lo.y);
+  v.hi = make_float2((v.hi.x - mean) * rstd * g.hi.x + be.hi.x, (v.hi.y - mean) * rstd * g.hi.y + be.hi.y);
 }
 
 __device__ __forceinline__ void copy_params(float* dst, const float* src, int n, int tid) {
@@ -336,6 +300,16 @@ __device__ __forceinline__ void copy_params(float* dst, const float* src, int n,
   do {                                                       \
     if (do_prof && tid == 0) p.prof[(slot)] = clock64();     \
   } while (0)
+
+// Developer build (-DAMUSE_FINE_PROF): extra stamps inside the stages of layer 1 (slots 112..127).
+#ifdef AMUSE_FINE_PROF
+#define AMUSE_FINE(slot)                                                  \
+  do {                                                                    \
+    if (do_prof && layer == 1 && tid == 0) p.prof[(slot)] = clock64();    \
+  } while (0)
+#else
+#define AMUSE_FINE(slot) do { } while (0)
+#endif
 
 }  // namespace
 
@@ -371,10 +345,12 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t rank = cluster_ctarank();   // == attention head owned by this CTA
   const int cid = static_cast<int>(cluster_id_x());
+  const bool gw = warp < kGemmWarps;         // warps 0..7 run the GEMMs, warps 8..9 only epilogues
   const int rb = warp / KS, ks = warp % KS;  // GEMM role: row block, K slice
-  // reduce / epilogue role: warp w owns rows w and w + 8 (second one only when RT == 10 and w < 2)
-  const int row0 = warp, row1 = warp + 8;
-  const bool own0 = row0 < RT, own1 = row1 < RT;
+  // reduce / epilogue role: warp w owns activation row w -- one row per warp, so no warp carries a
+  // second row on the critical path of the ~40 epilogues per step
+  const int row0 = warp;
+  const bool own0 = row0 < RT;
   const int T = p.T;
   const int s_base = cid * p.S;
   const int S = min(p.S, p.B - s_base);      // clips of this cluster (>= 1 by grid construction)
@@ -443,34 +419,17 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   auto exchange_epilogue = [&](const float* bias, const float* resid, const float* lnp, float* dst2, int prof_slot,
                                bool do_prof) {
     if (own0) {
-      Row4 v[2];
-      v[0] = gather4<RT, KS>(RED, row0, lane);
-      send_row(s, xe, rank, row0, lane, v[0]);
-      v[1] = v[0];
-      if (own1) {
-        v[1] = gather4<RT, KS>(RED, row1, lane);
-        send_row(s, xe, rank, row1, lane, v[1]);
-      }
-      const Row4 b = ld_row4(bias, lane);
-      v[0] = add4(v[0], b);
-      if (resid) v[0] = add4(v[0], ld_row4(resid + row0 * 128, lane));
-      if (own1) {
-        v[1] = add4(v[1], b);
-        if (resid) v[1] = add4(v[1], ld_row4(resid + row1 * 128, lane));
-      }
+      Row4 v = gather4<RT, KS>(RED, row0, lane);
+      send_row(s, xe, rank, row0, lane, v);
+      v = add4(v, ld_row4(bias, lane));
+      if (resid) v = add4(v, ld_row4(resid + row0 * 128, lane));
       if (prof_slot >= 0 && prof_slot < 12 && do_prof && tid == 0) p.prof[prof_slot + 100] = clock64();   // layer 0 only
       exchange_wait(s, xe);
       if (prof_slot >= 0 && do_prof && tid == 0) p.prof[prof_slot] = clock64();
-      const float* ps = s.Ps(xe & 1);
-      v[0] = add_peers(ps, row0, lane, v[0]);
-      if (own1) v[1] = add_peers(ps, row1, lane, v[1]);
-      if (lnp) layernorm2(v, lnp, lane);
-      st_row4(Xs + row0 * 128, lane, v[0]);
-      if (dst2) st_row4(dst2 + row0 * 128, lane, v[0]);
-      if (own1) {
-        st_row4(Xs + row1 * 128, lane, v[1]);
-        if (dst2) st_row4(dst2 + row1 * 128, lane, v[1]);
-      }
+      v = add_peers(s.Ps(xe & 1), row0, lane, v);
+      if (lnp) layernorm1(v, lnp, lane);
+      st_row4(Xs + row0 * 128, lane, v);
+      if (dst2) st_row4(dst2 + row0 * 128, lane, v);
     }
     ++xe;
     __syncthreads();
@@ -482,16 +441,14 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   auto exchange_epilogue_pruned = [&](const float* bias, const float* lnp, int prof_slot, bool do_prof) {
     if (warp < RB) {
       const int arow = warp * T;
-      Row4 v[2];
-      v[0] = gather4<RB, 8>(RED, warp, lane);
-      send_row(s, xe, rank, arow, lane, v[0]);
-      v[0] = add4(add4(v[0], ld_row4(bias, lane)), ld_row4(Xs + arow * 128, lane));
+      Row4 v = gather4<RB, 8>(RED, warp, lane);
+      send_row(s, xe, rank, arow, lane, v);
+      v = add4(add4(v, ld_row4(bias, lane)), ld_row4(Xs + arow * 128, lane));
       exchange_wait(s, xe);
       if (prof_slot >= 0 && do_prof && tid == 0) p.prof[prof_slot] = clock64();
-      v[0] = add_peers(s.Ps(xe & 1), arow, lane, v[0]);
-      v[1] = v[0];
-      layernorm2(v, lnp, lane);
-      st_row4(Xs + arow * 128, lane, v[0]);
+      v = add_peers(s.Ps(xe & 1), arow, lane, v);
+      layernorm1(v, lnp, lane);
+      st_row4(Xs + arow * 128, lane, v);
     }
     ++xe;
     __syncthreads();
@@ -541,10 +498,12 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         copy_params(par_tail, wt + 64 * 128, 128, tid);
         // my K slice of cat(x, skip): ranks 0,1 -> x[:, 64*rank ..], ranks 2,3 -> skip[:, 64*(rank-2) ..]
         const float* src = (rank < 2) ? (Xs + rank * 64) : (SK + (8 - layer) * kRMax * 128 + (rank - 2) * 64);
-        float acc[5][4];
-        gemm5<128, 4, (64 / KS) / 4>(src + (rb * 5) * 128 + ks * (64 / KS), 128,
-                                     wt + (ks * (32 / KS)) * 256 + lane * 2, acc);
-        park4<RT>(RED, rb, ks, lane, acc);
+        if (gw) {
+          float acc[5][4];
+          gemm5<128, 4, (64 / KS) / 4>(src + (rb * 5) * 128 + ks * (64 / KS), 128,
+                                       wt + (ks * (32 / KS)) * 256 + lane * 2, acc);
+          park4<RT>(RED, rb, ks, lane, acc);
+        }
         __syncthreads();
         wp_release(s, wp, tid);
         exchange_epilogue(par_tail, nullptr, nullptr, nullptr, -1, do_prof);
@@ -554,11 +513,13 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       // =============== QKV of my head (cross_attention.py:264-266, nn.MultiheadAttention in_proj)
       {
         const float* wt = wp_acquire(s, wp);
+        AMUSE_FINE(120);
         copy_params(par_bqkv, wt + 128 * 96, 96, tid);
-        float acc[5][3];
-        gemm5<96, 3, (128 / KS) / 4>(Xs + (rb * 5) * 128 + ks * (128 / KS), 128,
-                                     wt + (ks * (64 / KS)) * 192 + lane * 2, acc);
-        {
+        if (gw) {
+          float acc[5][3];
+          gemm5<96, 3, (128 / KS) / 4>(Xs + (rb * 5) * 128 + ks * (128 / KS), 128,
+                                       wt + (ks * (64 / KS)) * 192 + lane * 2, acc);
+          AMUSE_FINE(121);
           float* dst = RED + ((ks * RT + rb * 5) * 96) + lane;
 #pragma unroll
           for (int i = 0; i < 5; ++i) {
@@ -568,25 +529,23 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
           }
         }
         __syncthreads();
+        AMUSE_FINE(122);
         wp_release(s, wp, tid);
+        if (own0) {
+          float q = par_bqkv[lane], k = par_bqkv[32 + lane], v = par_bqkv[64 + lane];
 #pragma unroll
-        for (int o = 0; o < 2; ++o) {
-          const int row = o ? row1 : row0;
-          if (o ? own1 : own0) {
-            float q = par_bqkv[lane], k = par_bqkv[32 + lane], v = par_bqkv[64 + lane];
-#pragma unroll
-            for (int c = 0; c < KS; ++c) {
-              const float* src = RED + ((c * RT + row) * 96) + lane;
-              q += src[0];
-              k += src[32];
-              v += src[64];
-            }
-            float* dst = QKVs + row * kQkvLd + lane;
-            dst[0] = q * 0.17677669529663687f;   // nn.MultiheadAttention scales q (after bias) by head_dim^-0.5
-            dst[32] = k;
-            dst[64] = v;
+          for (int c = 0; c < KS; ++c) {
+            const float* src = RED + ((c * RT + row0) * 96) + lane;
+            q += src[0];
+            k += src[32];
+            v += src[64];
           }
+          float* dst = QKVs + row0 * kQkvLd + lane;
+          dst[0] = q * 0.17677669529663687f;   // nn.MultiheadAttention scales q (after bias) by head_dim^-0.5
+          dst[32] = k;
+          dst[64] = v;
         }
+        AMUSE_FINE(123);
         __syncthreads();
       }
       AMUSE_PROF(2 + layer * 10 + 1);
@@ -652,9 +611,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
           const float* wt = wp_acquire(s, wp);
           exchange_arm<RB>(s, xe, tid);
           copy_params(par_tail, wt + 32 * 128, kTileTail, tid);
-          float acc[RB][4];
-          gemm_rows<RB, 128, 4, 1>(Oh + warp * 4, T * kOhLd, wt + (warp * 2) * 256 + lane * 2, acc);
-          park_rows<RB>(RED, warp, lane, acc);
+          if (gw) {
+            float acc[RB][4];
+            gemm_rows<RB, 128, 4, 1>(Oh + warp * 4, T * kOhLd, wt + (warp * 2) * 256 + lane * 2, acc);
+            park_rows<RB>(RED, warp, lane, acc);
+          }
           __syncthreads();
           wp_release(s, wp, tid);
           exchange_epilogue_pruned(par_tail, par_tail + 128, 2 + layer * 10 + 3, do_prof);
@@ -663,9 +624,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         {   // FFN1 + erf-GELU
           const float* wt = wp_acquire(s, wp);
           copy_params(par_tail, wt + 128 * 128, 128, tid);
-          float acc[RB][4];
-          gemm_rows<RB, 128, 4, 4>(Xs + warp * 16, T * 128, wt + (warp * 8) * 256 + lane * 2, acc);
-          park_rows<RB>(RED, warp, lane, acc);
+          if (gw) {
+            float acc[RB][4];
+            gemm_rows<RB, 128, 4, 4>(Xs + warp * 16, T * 128, wt + (warp * 8) * 256 + lane * 2, acc);
+            park_rows<RB>(RED, warp, lane, acc);
+          }
           __syncthreads();
           wp_release(s, wp, tid);
           if (warp < RB) {
@@ -681,9 +644,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
           const float* wt = wp_acquire(s, wp);
           exchange_arm<RB>(s, xe, tid);
           copy_params(par_tail, wt + 128 * 128, kTileTail, tid);
-          float acc[RB][4];
-          gemm_rows<RB, 128, 4, 4>(Hs + warp * 16, T * 128, wt + (warp * 8) * 256 + lane * 2, acc);
-          park_rows<RB>(RED, warp, lane, acc);
+          if (gw) {
+            float acc[RB][4];
+            gemm_rows<RB, 128, 4, 4>(Hs + warp * 16, T * 128, wt + (warp * 8) * 256 + lane * 2, acc);
+            park_rows<RB>(RED, warp, lane, acc);
+          }
           __syncthreads();
           wp_release(s, wp, tid);
           exchange_epilogue_pruned(par_tail, par_tail + 128, 2 + layer * 10 + 6, do_prof);
@@ -694,13 +659,18 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       // =============== out_proj, K-split by head -> st.async partial exchange -> sum + LN1
       {
         const float* wt = wp_acquire(s, wp);
+        AMUSE_FINE(124);
         exchange_arm<RT>(s, xe, tid);
         copy_params(par_tail, wt + 32 * 128, kTileTail, tid);
-        float acc[5][4];
-        gemm5<128, 4, (32 / KS) / 4>(Oh + (rb * 5) * kOhLd + ks * (32 / KS), kOhLd,
-                                     wt + (ks * (16 / KS)) * 256 + lane * 2, acc);
-        park4<RT>(RED, rb, ks, lane, acc);
+        if (gw) {
+          float acc[5][4];
+          gemm5<128, 4, (32 / KS) / 4>(Oh + (rb * 5) * kOhLd + ks * (32 / KS), kOhLd,
+                                       wt + (ks * (16 / KS)) * 256 + lane * 2, acc);
+          AMUSE_FINE(125);
+          park4<RT>(RED, rb, ks, lane, acc);
+        }
         __syncthreads();
+        AMUSE_FINE(126);
         wp_release(s, wp, tid);
         exchange_epilogue(par_tail, Xs, par_tail + 128, nullptr, 2 + layer * 10 + 3, do_prof);
       }
@@ -709,24 +679,25 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       // =============== FFN1: my 128 hidden units, erf-GELU
       {
         const float* wt = wp_acquire(s, wp);
+        AMUSE_FINE(112);
         copy_params(par_tail, wt + 128 * 128, 128, tid);
-        float acc[5][4];
-        gemm5<128, 4, (128 / KS) / 4>(Xs + (rb * 5) * 128 + ks * (128 / KS), 128,
-                                      wt + (ks * (64 / KS)) * 256 + lane * 2, acc);
-        park4<RT>(RED, rb, ks, lane, acc);
-        __syncthreads();
-        wp_release(s, wp, tid);
-        const Row4 b = ld_row4(par_tail, lane);
-#pragma unroll
-        for (int o = 0; o < 2; ++o) {
-          const int row = o ? row1 : row0;
-          if (o ? own1 : own0) {
-            Row4 v = add4(gather4<RT, KS>(RED, row, lane), b);
-            v.lo = make_float2(gelu_erf(v.lo.x), gelu_erf(v.lo.y));
-            v.hi = make_float2(gelu_erf(v.hi.x), gelu_erf(v.hi.y));
-            st_row4(Hs + row * 128, lane, v);
-          }
+        if (gw) {
+          float acc[5][4];
+          gemm5<128, 4, (128 / KS) / 4>(Xs + (rb * 5) * 128 + ks * (128 / KS), 128,
+                                        wt + (ks * (64 / KS)) * 256 + lane * 2, acc);
+          AMUSE_FINE(113);
+          park4<RT>(RED, rb, ks, lane, acc);
         }
+        __syncthreads();
+        AMUSE_FINE(114);
+        wp_release(s, wp, tid);
+        if (own0) {
+          Row4 v = add4(gather4<RT, KS>(RED, row0, lane), ld_row4(par_tail, lane));
+          v.lo = make_float2(gelu_erf(v.lo.x), gelu_erf(v.lo.y));
+          v.hi = make_float2(gelu_erf(v.hi.x), gelu_erf(v.hi.y));
+          st_row4(Hs + row0 * 128, lane, v);
+        }
+        AMUSE_FINE(115);
         __syncthreads();
       }
       AMUSE_PROF(2 + layer * 10 + 5);
@@ -734,13 +705,18 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       // =============== FFN2, K-split over my 128 hidden units -> exchange -> sum + LN2
       {
         const float* wt = wp_acquire(s, wp);
+        AMUSE_FINE(116);
         exchange_arm<RT>(s, xe, tid);
         copy_params(par_tail, wt + 128 * 128, kTileTail, tid);
-        float acc[5][4];
-        gemm5<128, 4, (128 / KS) / 4>(Hs + (rb * 5) * 128 + ks * (128 / KS), 128,
-                                      wt + (ks * (64 / KS)) * 256 + lane * 2, acc);
-        park4<RT>(RED, rb, ks, lane, acc);
+        if (gw) {
+          float acc[5][4];
+          gemm5<128, 4, (128 / KS) / 4>(Hs + (rb * 5) * 128 + ks * (128 / KS), 128,
+                                        wt + (ks * (64 / KS)) * 256 + lane * 2, acc);
+          AMUSE_FINE(117);
+          park4<RT>(RED, rb, ks, lane, acc);
+        }
         __syncthreads();
+        AMUSE_FINE(118);
         wp_release(s, wp, tid);
         exchange_epilogue(par_tail, Xs, par_tail + 128, (layer < 4) ? (SK + layer * kRMax * 128) : nullptr,
                           2 + layer * 10 + 6, do_prof);
@@ -784,8 +760,15 @@ cudaError_t launch(const Params& p, cudaStream_t stream) {
   using Kernel = void (*)(const Params);
   static const Kernel kernels[2][2] = {{denoise_loop_kernel<1, false>, denoise_loop_kernel<1, true>},
                                        {denoise_loop_kernel<2, false>, denoise_loop_kernel<2, true>}};
-  static bool configured = false;
+  static bool configured_dev[64] = {};   // attributes and __constant__ data are per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool& configured = configured_dev[dev & 63];
   if (!configured) {
+    int2 tab[kTilesPerStep];
+    for (int i = 0; i < kTilesPerStep; ++i) tile_info(i, tab[i].x, tab[i].y);
+    cudaError_t e0 = cudaMemcpyToSymbol(c_tile_tab, tab, sizeof(tab));
+    if (e0 != cudaSuccess) return e0;
     for (int i = 0; i < 4; ++i) {
       cudaError_t e = cudaFuncSetAttribute(kernels[i >> 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(smem_bytes()));

@@ -7,7 +7,8 @@ namespace amuse {
 namespace dn {
 
 constexpr int kCluster = 4;            // CTAs per thread-block cluster = attention heads (one head per CTA)
-constexpr int kThreads = 256;
+constexpr int kThreads = 320;        // 8 GEMM warps (row block x K slice) + 2: ten warps = one per activation row in the epilogues
+constexpr int kGemmWarps = 8;
 constexpr int kSMax = 2;               // clips per cluster
 constexpr int kTMax = 5;               // tokens per clip: z, t, con, emo, sty (denoiser.py:174,180)
 constexpr int kRMax = kSMax * kTMax;   // activation rows per cluster

@@ -61,6 +61,15 @@ def main():
         print(f"layer {l}: " + " ".join(f"{n}={c}" for n, c in zip(names, row)))
     print("final+update:", st[92] - st[2 + 8 * 10 + 7])
     print("layer0 exchange waits: out_proj", st[5] - st[105], " ffn2", st[8] - st[108])
+    if st[112]:   # library built with -DAMUSE_FINE_PROF: inside the stages of layer 1 (thread 0)
+        print(f"fine qkv : acquire={st[120] - st[12]} gemm={st[121] - st[120]} park+sync={st[122] - st[121]} "
+              f"gather={st[123] - st[122]} sync={st[13] - st[123]}")
+        print(f"fine oprj: acquire={st[124] - st[14]} gemm={st[125] - st[124]} park+sync={st[126] - st[125]} "
+              f"gather+send+wait={st[15] - st[126]} sum+ln+sync={st[16] - st[15]}")
+        print(f"fine ffn1: acquire={st[112] - st[16]} gemm={st[113] - st[112]} park+sync={st[114] - st[113]} "
+              f"gather+gelu={st[115] - st[114]} sync={st[17] - st[115]}")
+        print(f"fine ffn2: acquire={st[116] - st[17]} gemm={st[117] - st[116]} park+sync={st[118] - st[117]} "
+              f"gather+send+wait={st[18] - st[118]} sum+ln+sync={st[19] - st[18]}")
 
 
 if __name__ == "__main__":
