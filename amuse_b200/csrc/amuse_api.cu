@@ -128,6 +128,7 @@ struct amuse_ctx {
   DevBuf eFeat, eEmb;            // encoder: packed feature planes [rows][352] x 2, embedded frames [rows][128]
   bool dec_use_tc = true;        // decoder GEMMs on tcgen05 (3xTF32); false = fp32 FFMA kernels
   int prune_last = 1;            // denoise loop: last layer for token 0 only (AMUSE_PRUNE_LAST=0 disables; tuning hook)
+  int wide_rows = 0;             // denoise loop: 10-row GEMM warps in 2-clip clusters (AMUSE_WIDE_ROWS=0/1; tuning hook)
   DevBuf h2d;   // staging for the *_host entry point
   DevBuf mel_t; // [257][128] mel filterbank weights (K-major)
   long long* d_prof = nullptr;
@@ -670,6 +671,7 @@ int run_denoise(amuse_ctx* ctx, int B, Schedule& sc, int clip, const float* late
   p.seed = seed;
   p.seed_elem_base = elem_base;
   p.prune_last = ctx->prune_last;
+  p.wide_rows = ctx->wide_rows;
   CU(dn::launch(p, st));
   ctx->launches++;
   ctx->prof_step = -1;
@@ -1071,6 +1073,7 @@ int amuse_create(amuse_ctx** out, int device_ordinal) {
   default_alphas(c->alphas_cumprod);
   if (const char* e = getenv("AMUSE_DECODE_FFMA")) c->dec_use_tc = !(e[0] == '1');   // A/B switch for measurements
   if (const char* e = getenv("AMUSE_PRUNE_LAST")) c->prune_last = (e[0] != '0');
+  if (const char* e = getenv("AMUSE_WIDE_ROWS")) c->wide_rows = (e[0] != '0');
   if (cudaMalloc(&c->d_prof, 128 * sizeof(long long)) != cudaSuccess) {
     delete c;
     return AMUSE_E_CUDA;

@@ -51,7 +51,9 @@ static_assert(kQkvOhFloats >= kRMax * 128, "Hs aliases the q|k|v + attention-out
 // ---------------------------------------------------------------- shared-memory carve-up
 // Offsets (floats) from the dynamic shared-memory base.  Every pointer is formed as
 // `smem + constant`, so the compiler keeps the .shared address space (LDS/STS, not generic LD/ST).
-constexpr int kActFloats = kRMax * 128 + 4 * kRMax * 128 + 2 * kPsFloats + kQkvOhFloats + kRedFloats +
+constexpr int kRedSlot = kRMax * 128;        // one K-slice's partial tile: 10 rows x 128 (WIDE layout, see the kernel)
+static_assert(kRedFloats == 4 * kRedSlot && kPsFloats == 3 * kRedSlot, "WIDE slot map: 4 in RED, 3 in the idle Ps buffer, 1 extra");
+constexpr int kActFloats = kRMax * 128 + 4 * kRMax * 128 + 2 * kPsFloats + kQkvOhFloats + kRedFloats + kRedSlot +
                            kSMax * 3 * 128 + 256 + kSMax * 128 + kSMax * 128 + 128 + 256 + 96 + kTileTail;
 constexpr int kSmemFloats = 2 * kWBufFloats + kActFloats + 16 /*mbarriers + pad*/;
 static_assert(kSmemFloats * 4 <= 232448, "exceeds the 227 KB shared-memory limit of sm_100");
@@ -68,7 +70,8 @@ struct Smem {
   static constexpr int oHs = oQKV;                           // [10][128] my 128 hidden units -- ALIASES q|k|v/Oh
                                                              // (dead between out_proj and the next layer's QKV)
   static constexpr int oRED = oQKV + kQkvOhFloats;           // K-split partial sums
-  static constexpr int oCs = oRED + kRedFloats;              // [2][3][128] condition tokens (+PE)
+  static constexpr int oRed7 = oRED + kRedFloats;            // [10][128] eighth K-slice of the WIDE layout
+  static constexpr int oCs = oRed7 + kRedSlot;               // [2][3][128] condition tokens (+PE)
   static constexpr int oPe = oCs + kSMax * 3 * 128;          // [2][128]
   static constexpr int oZs = oPe + 256;                      // [2][128] current latents
   static constexpr int oEs = oZs + kSMax * 128;              // [2][128] eps
@@ -319,11 +322,23 @@ __device__ __forceinline__ void copy_params(float* dst, const float* src, int n,
 // so its out_proj / FFN1 / FFN2 are evaluated for RB rows instead of 5*RB: all 8 warps split K, every
 // weight tile is read from shared memory once, and the exchanges carry RB rows.  K and V of the last
 // layer still need all tokens, so the skip-linear, QKV and attention stages are unchanged.
-template <int RB, bool PRUNE>
+// WIDE (RB == 2 only): instead of 2 row blocks x 4 K slices, every GEMM warp computes all 10 rows over 1/8
+// of K.  Each weight word is then read from shared memory once per CTA instead of twice and a warp issues 80
+// FFMA2 per 18 shared-memory loads instead of 40 per 13: with 5-row warps the LDS pipe is as busy as the FMA
+// pipe (8 warps x 27 LSU cycles vs 2 warps/SMSP x 40 x 2.75 issue cycles per 4-k round).  The price is 8 partial
+// tiles to park instead of 4; the 4 extra slots live in the Ps receive buffer of the exchange AFTER the next
+// one (3 slots) and in one extra 5 KB buffer.  That Ps buffer is idle: with X = the next exchange this CTA
+// will send, peers may already be writing X data into Ps[X & 1], but nobody can send X+1 data before it has
+// received this CTA's X rows, and every row is sent by its owner warp after that warp's last read of the
+// parked partials (the sent value depends on those loads).  The previous contents (exchange X-1) were consumed
+// before the __syncthreads() that ended that exchange's epilogue.
+template <int RB, bool PRUNE, bool WIDE>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     denoise_loop_kernel(const Params p) {
-  constexpr int KS = 8 / RB;      // K-split factor of every GEMM
-  constexpr int RT = RB * 5;      // activation rows computed by the GEMMs
+  static_assert(!WIDE || RB == 2, "WIDE is the 2-clip layout");
+  constexpr int KS = WIDE ? 8 : 8 / RB;   // K-split factor of every GEMM
+  constexpr int RT = RB * 5;              // activation rows computed by the GEMMs
+  constexpr int NRW = WIDE ? 10 : 5;      // rows per GEMM warp
   extern __shared__ __align__(128) float smem_raw[];
   Smem s;
   s.base = smem_raw;
@@ -346,7 +361,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   const uint32_t rank = cluster_ctarank();   // == attention head owned by this CTA
   const int cid = static_cast<int>(cluster_id_x());
   const bool gw = warp < kGemmWarps;         // warps 0..7 run the GEMMs, warps 8..9 only epilogues
-  const int rb = warp / KS, ks = warp % KS;  // GEMM role: row block, K slice
+  const int rb = WIDE ? 0 : warp / KS, ks = warp % KS;  // GEMM role: row block, K slice
   // reduce / epilogue role: warp w owns activation row w -- one row per warp, so no warp carries a
   // second row on the critical path of the ~40 epilogues per step
   const int row0 = warp;
@@ -414,12 +429,44 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   const int at_src = at_slot * 10;                             // lane holding (j = 0, c = 0) of my slot
   const bool at_pv = at_live && at_l < 8;
 
+  // Parked K-split partials.  WIDE: slot q of 8 (see the kernel comment); otherwise RED[ks][RT][128].
+  auto wslot = [&](int q) -> float* {
+    const int off = (q < 4) ? Smem::oRED + q * kRedSlot
+                            : (q < 7) ? Smem::oPs + static_cast<int>((xe + 1) & 1) * kPsFloats + (q - 4) * kRedSlot
+                                      : Smem::oRed7;
+    return s.at(off);
+  };
+  auto park_tile = [&](const float (&acc)[NRW][4]) {
+    if constexpr (WIDE) {
+      float* dst = wslot(ks);
+#pragma unroll
+      for (int i = 0; i < NRW; ++i) {
+        Row4 v;
+        v.lo = make_float2(acc[i][0], acc[i][1]);
+        v.hi = make_float2(acc[i][2], acc[i][3]);
+        st_row4(dst + i * 128, lane, v);
+      }
+    } else {
+      park4<RT>(RED, rb, ks, lane, acc);
+    }
+  };
+  auto gather_row = [&](int row) -> Row4 {
+    if constexpr (WIDE) {
+      Row4 v = ld_row4(wslot(0) + row * 128, lane);
+#pragma unroll
+      for (int q = 1; q < 8; ++q) v = add4(v, ld_row4(wslot(q) + row * 128, lane));
+      return v;
+    } else {
+      return gather4<RT, KS>(RED, row, lane);
+    }
+  };
+
   // K-split partial -> st.async exchange -> sum + bias [+ residual] [+ LayerNorm] -> Xs [, skip stack].
   // A lambda so that the three users (skip fusion, out_proj, FFN2) share one source form.
   auto exchange_epilogue = [&](const float* bias, const float* resid, const float* lnp, float* dst2, int prof_slot,
                                bool do_prof) {
     if (own0) {
-      Row4 v = gather4<RT, KS>(RED, row0, lane);
+      Row4 v = gather_row(row0);
       send_row(s, xe, rank, row0, lane, v);
       v = add4(v, ld_row4(bias, lane));
       if (resid) v = add4(v, ld_row4(resid + row0 * 128, lane));
@@ -499,10 +546,10 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         // my K slice of cat(x, skip): ranks 0,1 -> x[:, 64*rank ..], ranks 2,3 -> skip[:, 64*(rank-2) ..]
         const float* src = (rank < 2) ? (Xs + rank * 64) : (SK + (8 - layer) * kRMax * 128 + (rank - 2) * 64);
         if (gw) {
-          float acc[5][4];
-          gemm5<128, 4, (64 / KS) / 4>(src + (rb * 5) * 128 + ks * (64 / KS), 128,
-                                       wt + (ks * (32 / KS)) * 256 + lane * 2, acc);
-          park4<RT>(RED, rb, ks, lane, acc);
+          float acc[NRW][4];
+          gemm_rows<NRW, 128, 4, (64 / KS) / 4>(src + (rb * 5) * 128 + ks * (64 / KS), 128,
+                                                wt + (ks * (32 / KS)) * 256 + lane * 2, acc);
+          park_tile(acc);
         }
         __syncthreads();
         wp_release(s, wp, tid);
@@ -516,13 +563,13 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         AMUSE_FINE(120);
         copy_params(par_bqkv, wt + 128 * 96, 96, tid);
         if (gw) {
-          float acc[5][3];
-          gemm5<96, 3, (128 / KS) / 4>(Xs + (rb * 5) * 128 + ks * (128 / KS), 128,
-                                       wt + (ks * (64 / KS)) * 192 + lane * 2, acc);
+          float acc[NRW][3];
+          gemm_rows<NRW, 96, 3, (128 / KS) / 4>(Xs + (rb * 5) * 128 + ks * (128 / KS), 128,
+                                                wt + (ks * (64 / KS)) * 192 + lane * 2, acc);
           AMUSE_FINE(121);
-          float* dst = RED + ((ks * RT + rb * 5) * 96) + lane;
+          float* dst = (WIDE ? wslot(ks) : RED + ((ks * RT + rb * 5) * 96)) + lane;
 #pragma unroll
-          for (int i = 0; i < 5; ++i) {
+          for (int i = 0; i < NRW; ++i) {
             dst[i * 96] = acc[i][0];
             dst[i * 96 + 32] = acc[i][1];
             dst[i * 96 + 64] = acc[i][2];
@@ -535,7 +582,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
           float q = par_bqkv[lane], k = par_bqkv[32 + lane], v = par_bqkv[64 + lane];
 #pragma unroll
           for (int c = 0; c < KS; ++c) {
-            const float* src = RED + ((c * RT + row0) * 96) + lane;
+            const float* src = (WIDE ? wslot(c) + row0 * 96 : RED + ((c * RT + row0) * 96)) + lane;
             q += src[0];
             k += src[32];
             v += src[64];
@@ -663,11 +710,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         exchange_arm<RT>(s, xe, tid);
         copy_params(par_tail, wt + 32 * 128, kTileTail, tid);
         if (gw) {
-          float acc[5][4];
-          gemm5<128, 4, (32 / KS) / 4>(Oh + (rb * 5) * kOhLd + ks * (32 / KS), kOhLd,
-                                       wt + (ks * (16 / KS)) * 256 + lane * 2, acc);
+          float acc[NRW][4];
+          gemm_rows<NRW, 128, 4, (32 / KS) / 4>(Oh + (rb * 5) * kOhLd + ks * (32 / KS), kOhLd,
+                                                wt + (ks * (16 / KS)) * 256 + lane * 2, acc);
           AMUSE_FINE(125);
-          park4<RT>(RED, rb, ks, lane, acc);
+          park_tile(acc);
         }
         __syncthreads();
         AMUSE_FINE(126);
@@ -682,17 +729,17 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         AMUSE_FINE(112);
         copy_params(par_tail, wt + 128 * 128, 128, tid);
         if (gw) {
-          float acc[5][4];
-          gemm5<128, 4, (128 / KS) / 4>(Xs + (rb * 5) * 128 + ks * (128 / KS), 128,
-                                        wt + (ks * (64 / KS)) * 256 + lane * 2, acc);
+          float acc[NRW][4];
+          gemm_rows<NRW, 128, 4, (128 / KS) / 4>(Xs + (rb * 5) * 128 + ks * (128 / KS), 128,
+                                                 wt + (ks * (64 / KS)) * 256 + lane * 2, acc);
           AMUSE_FINE(113);
-          park4<RT>(RED, rb, ks, lane, acc);
+          park_tile(acc);
         }
         __syncthreads();
         AMUSE_FINE(114);
         wp_release(s, wp, tid);
         if (own0) {
-          Row4 v = add4(gather4<RT, KS>(RED, row0, lane), ld_row4(par_tail, lane));
+          Row4 v = add4(gather_row(row0), ld_row4(par_tail, lane));
           v.lo = make_float2(gelu_erf(v.lo.x), gelu_erf(v.lo.y));
           v.hi = make_float2(gelu_erf(v.hi.x), gelu_erf(v.hi.y));
           st_row4(Hs + row0 * 128, lane, v);
@@ -709,11 +756,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         exchange_arm<RT>(s, xe, tid);
         copy_params(par_tail, wt + 128 * 128, kTileTail, tid);
         if (gw) {
-          float acc[5][4];
-          gemm5<128, 4, (128 / KS) / 4>(Hs + (rb * 5) * 128 + ks * (128 / KS), 128,
-                                        wt + (ks * (64 / KS)) * 256 + lane * 2, acc);
+          float acc[NRW][4];
+          gemm_rows<NRW, 128, 4, (128 / KS) / 4>(Hs + (rb * 5) * 128 + ks * (128 / KS), 128,
+                                                 wt + (ks * (64 / KS)) * 256 + lane * 2, acc);
           AMUSE_FINE(117);
-          park4<RT>(RED, rb, ks, lane, acc);
+          park_tile(acc);
         }
         __syncthreads();
         AMUSE_FINE(118);
@@ -758,8 +805,9 @@ size_t smem_bytes() { return static_cast<size_t>(kSmemFloats) * sizeof(float); }
 
 cudaError_t launch(const Params& p, cudaStream_t stream) {
   using Kernel = void (*)(const Params);
-  static const Kernel kernels[2][2] = {{denoise_loop_kernel<1, false>, denoise_loop_kernel<1, true>},
-                                       {denoise_loop_kernel<2, false>, denoise_loop_kernel<2, true>}};
+  static const Kernel kernels[3][2] = {{denoise_loop_kernel<1, false, false>, denoise_loop_kernel<1, true, false>},
+                                       {denoise_loop_kernel<2, false, false>, denoise_loop_kernel<2, true, false>},
+                                       {denoise_loop_kernel<2, false, true>, denoise_loop_kernel<2, true, true>}};
   static bool configured_dev[64] = {};   // attributes and __constant__ data are per device
   int dev = 0;
   cudaGetDevice(&dev);
@@ -769,7 +817,7 @@ cudaError_t launch(const Params& p, cudaStream_t stream) {
     for (int i = 0; i < kTilesPerStep; ++i) tile_info(i, tab[i].x, tab[i].y);
     cudaError_t e0 = cudaMemcpyToSymbol(c_tile_tab, tab, sizeof(tab));
     if (e0 != cudaSuccess) return e0;
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 6; ++i) {
       cudaError_t e = cudaFuncSetAttribute(kernels[i >> 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(smem_bytes()));
       if (e != cudaSuccess) return e;
@@ -778,7 +826,7 @@ cudaError_t launch(const Params& p, cudaStream_t stream) {
   }
   if (p.S < 1 || p.S > kSMax) return cudaErrorInvalidValue;
   const int n_clusters = (p.B + p.S - 1) / p.S;
-  kernels[p.S - 1][p.prune_last ? 1 : 0]<<<dim3(n_clusters * kCluster), dim3(kThreads), smem_bytes(), stream>>>(p);
+  kernels[(p.S == 2 && p.wide_rows) ? 2 : p.S - 1][p.prune_last ? 1 : 0]<<<dim3(n_clusters * kCluster), dim3(kThreads), smem_bytes(), stream>>>(p);
   return cudaGetLastError();
 }
 

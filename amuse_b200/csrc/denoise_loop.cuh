@@ -71,6 +71,7 @@ struct Params {
   unsigned long long seed_elem_base;   // global index of this launch's first latent element (multi-GPU shards)
   int prof_step;
   int prune_last;            // last layer evaluated for token 0 only (same result; see denoise_loop.cu PRUNE)
+  int wide_rows;             // 2-clip clusters: every GEMM warp computes all 10 rows over 1/8 of K (see denoise_loop.cu WIDE)
 };
 
 size_t smem_bytes();
