@@ -237,6 +237,10 @@ __device__ __forceinline__ Row4 gather4(const float* RED, int row, int lane) {
 // running exchange index xe (buffer = xe & 1): a peer can only start exchange xe+2 (same buffer)
 // after it completed xe+1, which needs MY xe+1 data, which I send after I have consumed xe -- so a
 // buffer is never overwritten before it has been read, and phases never mix.
+// Cost (scripts/ubench_dsmem.cu, measured): ~290 cycles + bytes / 21.6 B/clk per exchange -- 1000 cycles for
+// the 15 KB a CTA sends and receives here, 650 for 7.5 KB, 460 for 3.75 KB; st.async.v4 is no faster than .v2
+// and cp.async.bulk shared::cta -> shared::cluster is 10% slower, so the volume is what matters.  mapa compiles
+// to one PRMT, hoisting it out of the loop was measured slightly slower (63.3 vs 62.5 us/step).
 __device__ __forceinline__ void st_async_f2(uint32_t dst, float2 v, uint32_t mbar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(dst),
                "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(mbar)
@@ -251,36 +255,6 @@ __device__ __forceinline__ void send_row(const Smem& s, uint32_t xe, uint32_t ra
     const uint32_t slot = (rank < peer) ? rank : rank - 1;   // my slot in the peer's [3][rows][128] buffer
     const uint32_t dst = map_to_rank(ps + (slot * kRMax + row) * 128 + 2 * lane, peer);
     const uint32_t rbar = map_to_rank(bar, peer);
-    st_async_f2(dst, v.lo, rbar);
-    st_async_f2(dst + 64 * 4, v.hi, rbar);
-  }
-}
-// AMUSE_HOIST_MAPA: the shared::cluster window is linear in the CTA-local offset, so one mapa per peer (of the
-// dynamic shared-memory base, done once before the loop) replaces the 6 per row and exchange above.
-struct PeerMap {
-  uint32_t base[kCluster - 1];   // shared::cluster address of peer (rank + d + 1)'s smem base
-  uint32_t slot_off[kCluster - 1];   // byte offset of my slot inside a peer's Ps buffer
-  uint32_t local;                // CTA-local shared address of the base
-};
-__device__ __forceinline__ PeerMap make_peer_map(const Smem& s, uint32_t rank) {
-  PeerMap m;
-  m.local = smem_u32(s.base);
-#pragma unroll
-  for (uint32_t d = 1; d < kCluster; ++d) {
-    const uint32_t peer = (rank + d) & (kCluster - 1);
-    const uint32_t slot = (rank < peer) ? rank : rank - 1;
-    m.base[d - 1] = map_to_rank(s.base, peer);
-    m.slot_off[d - 1] = slot * kRMax * 128 * 4;
-  }
-  return m;
-}
-__device__ __forceinline__ void send_row(const Smem& s, const PeerMap& m, uint32_t xe, int row, int lane, const Row4& v) {
-  const uint32_t ps_off = smem_u32(s.Ps(xe & 1) + row * 128 + 2 * lane) - m.local;
-  const uint32_t bar_off = smem_u32(s.xbar(xe & 1)) - m.local;
-#pragma unroll
-  for (uint32_t d = 0; d < kCluster - 1; ++d) {
-    const uint32_t dst = m.base[d] + m.slot_off[d] + ps_off;
-    const uint32_t rbar = m.base[d] + bar_off;
     st_async_f2(dst, v.lo, rbar);
     st_async_f2(dst + 64 * 4, v.hi, rbar);
   }
@@ -303,7 +277,8 @@ __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(
 // One butterfly instead of two: sum and sum of squares of d = x - c are reduced together, with the
 // shift c = first element of the row (one extra shuffle), so that var = E[d^2] - E[d]^2 does not
 // cancel (|E[d]| is of the order of the row's standard deviation, not of its mean).
-__device__ __forceinline__ void layernorm1(Row4& v, const Row4& g, const Row4& be) {
+__device__ __forceinline__ void layernorm1(Row4& v, const float* lnp, int lane) {
+  const Row4 g = ld_row4(lnp, lane), be = ld_row4(lnp + 128, lane);
   const float c = __shfl_sync(0xffffffffu, v.lo.x, 0);
   v.lo.x -= c;
   v.lo.y -= c;
@@ -322,21 +297,12 @@ __device__ __forceinline__ void layernorm1(Row4& v, const Row4& g, const Row4& b
   v.lo = make_float2((v.lo.x - mean) * rstd * g.lo.x + be.lo.x, (v.lo.y - mean) * rstd * g.lo.y + be.lo.y);
   v.hi = make_float2((v.hi.x - mean) * rstd * g.hi.x + be.hi.x, (v.hi.y - mean) * rstd * g.hi.y + be.hi.y);
 }
-__device__ __forceinline__ void layernorm1(Row4& v, const float* lnp, int lane) {
-  const Row4 g = ld_row4(lnp, lane), be = ld_row4(lnp + 128, lane);
-  layernorm1(v, g, be);
-}
 
 // The bias / LayerNorm vectors of a stage are copied out of the weight tile so that the ring slot can be handed
-// back to the TMA engine before the epilogue runs.  AMUSE_IDLE_COPY: only warps 8 and 9 copy -- they have no
-// GEMM role and would otherwise wait at the barrier, and the GEMM warps start their first loads earlier.
+// back to the TMA engine before the epilogue runs.  All 10 warps copy: leaving it to the two warps without a
+// GEMM role was measured 3% slower per step (64.5 vs 62.5 us), their 6 dependent LDS/STS rounds end after the GEMM.
 __device__ __forceinline__ void copy_params(float* dst, const float* src, int n, int tid) {
-#ifdef AMUSE_IDLE_COPY
-  if (tid >= kGemmWarps * 32)
-    for (int i = tid - kGemmWarps * 32; i < n; i += kThreads - kGemmWarps * 32) dst[i] = src[i];
-#else
   for (int i = tid; i < n; i += kThreads) dst[i] = src[i];
-#endif
 }
 
 
@@ -438,9 +404,6 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     wp_issue(s, wp, 1);
   }
   uint32_t xe = 0;   // running index of the DSMEM exchange (selects receive buffer + mbarrier phase)
-#ifdef AMUSE_HOIST_MAPA
-  const PeerMap pmap = make_peer_map(s, rank);
-#endif
   __syncthreads();
   cluster_sync_all();   // every CTA of the cluster is resident, zero-filled and has its mbarriers
                         // initialised before any peer stores into its shared memory
@@ -511,30 +474,14 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
                                bool do_prof) {
     if (own0) {
       Row4 v = gather_row(row0);
-#ifdef AMUSE_HOIST_MAPA
-      send_row(s, pmap, xe, row0, lane, v);
-#else
       send_row(s, xe, rank, row0, lane, v);
-#endif
       v = add4(v, ld_row4(bias, lane));
       if (resid) v = add4(v, ld_row4(resid + row0 * 128, lane));
       if (prof_slot >= 0 && prof_slot < 12 && do_prof && tid == 0) p.prof[prof_slot + 100] = clock64();   // layer 0 only
-#ifdef AMUSE_LN_PREFETCH
-      // LayerNorm weight / bias fetched while the peers' partials are in flight
-      Row4 g, be;
-      if (lnp) {
-        g = ld_row4(lnp, lane);
-        be = ld_row4(lnp + 128, lane);
-      }
-#endif
       exchange_wait(s, xe);
       if (prof_slot >= 0 && do_prof && tid == 0) p.prof[prof_slot] = clock64();
       v = add_peers(s.Ps(xe & 1), row0, lane, v);
-#ifdef AMUSE_LN_PREFETCH
-      if (lnp) layernorm1(v, g, be);
-#else
       if (lnp) layernorm1(v, lnp, lane);
-#endif
       st_row4(Xs + row0 * 128, lane, v);
       if (dst2) st_row4(dst2 + row0 * 128, lane, v);
     }
@@ -549,11 +496,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     if (warp < RB) {
       const int arow = warp * T;
       Row4 v = gather4<RB, 8>(RED, warp, lane);
-#ifdef AMUSE_HOIST_MAPA
-      send_row(s, pmap, xe, arow, lane, v);
-#else
       send_row(s, xe, rank, arow, lane, v);
-#endif
       v = add4(add4(v, ld_row4(bias, lane)), ld_row4(Xs + arow * 128, lane));
       exchange_wait(s, xe);
       if (prof_slot >= 0 && do_prof && tid == 0) p.prof[prof_slot] = clock64();

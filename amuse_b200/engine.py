@@ -92,6 +92,9 @@ class Engine:
             self._check(self.lib.amuse_finalize_weights(self._h, self._stream()))
         self._finalized = True
 
+    def _empty(self, *shape) -> torch.Tensor:
+        return torch.empty(*shape, device=self.device, dtype=torch.float32)
+
     def reserve(self, max_clips: int, max_steps: int = 1000):
         self._check(self.lib.amuse_reserve(self._h, max_clips, max_steps))
 
@@ -105,6 +108,8 @@ class Engine:
     def denoise(self, latents0, z_con, z_emo=None, z_sty=None, n_steps=50, sampler="ddim", eta=0.0,
                 clip_sample=None, step_noise=None, seed=0) -> torch.Tensor:
         B = latents0.shape[0]
+        if B == 0:   # an empty batch has nothing to launch; the reference returns empty tensors as well
+            return self._empty(0, 128)
         l0 = self._dev(latents0.reshape(B, 128), (B, 128))
         con, emo, sty = self._dev(z_con, (B, 256)), self._dev(z_emo, (B, 256)), self._dev(z_sty, (B, 256))
         noise = self._dev(step_noise, (n_steps, B, 128)) if step_noise is not None else None
@@ -128,6 +133,9 @@ class Engine:
 
     def decode(self, latents, want_feats=False):
         B = latents.shape[0]
+        if B == 0:
+            e = (self._empty(0, 300, 55, 3), self._empty(0, 300, 3))
+            return e + (self._empty(0, 300, 333),) if want_feats else e
         z = self._dev(latents.reshape(B, 128), (B, 128))
         poses = torch.empty(B, 300, 55, 3, device=self.device, dtype=torch.float32)
         trans = torch.empty(B, 300, 3, device=self.device, dtype=torch.float32)
@@ -140,6 +148,8 @@ class Engine:
     def encode(self, feats: torch.Tensor):
         """``MotionPrior.encode`` without the rsample draw: feats [B,300,333] -> (mu [B,128], logvar [B,128])."""
         B = feats.shape[0]
+        if B == 0:
+            return self._empty(0, 128), self._empty(0, 128)
         x = self._dev(feats, (B, 300, 333))
         mu, logvar = (torch.empty(B, 128, device=self.device, dtype=torch.float32) for _ in range(2))
         with torch.cuda.device(self.device):
@@ -170,6 +180,13 @@ class Engine:
                            clip_sample=None, step_noise=None, seed=0, want_latents=False, want_feats=False):
         """Device tensors in, device tensors out: {"poses": [B,300,55,3], "trans": [B,300,3]}."""
         B = latents0.shape[0]
+        if B == 0:
+            out = {"poses": self._empty(0, 300, 55, 3), "trans": self._empty(0, 300, 3)}
+            if want_latents:
+                out["latents"] = self._empty(0, 128)
+            if want_feats:
+                out["feats"] = self._empty(0, 300, 333)
+            return out
         l0 = self._dev(latents0.reshape(B, 128), (B, 128))
         con, emo, sty = self._dev(z_con, (B, 256)), self._dev(z_emo, (B, 256)), self._dev(z_sty, (B, 256))
         noise = self._dev(step_noise, (n_steps, B, 128)) if step_noise is not None else None
@@ -193,6 +210,8 @@ class Engine:
                                 clip_sample=None, step_noise=None, seed=0, out_poses=None, out_trans=None):
         """HOST tensors in (ideally pinned), HOST tensors out; copies are inside the call."""
         B = latents0.shape[0]
+        if B == 0:
+            return {"poses": torch.empty(0, 300, 55, 3, dtype=torch.float32), "trans": torch.empty(0, 300, 3, dtype=torch.float32)}
         h = lambda t: None if t is None else t.detach().to(dtype=torch.float32).contiguous()
         l0, con, emo, sty, noise = h(latents0.reshape(B, 128)), h(z_con), h(z_emo), h(z_sty), h(step_noise)
         for t in (l0, con, emo, sty, noise):
@@ -220,6 +239,8 @@ class Engine:
 
     def ast_features(self, fbank: torch.Tensor):
         B = fbank.shape[0]
+        if B == 0:
+            return self._empty(0, 256), self._empty(0, 256), self._empty(0, 256)
         x = self._dev(fbank, (B, 1024, 128))
         con, emo, sty = (torch.empty(B, 256, device=self.device, dtype=torch.float32) for _ in range(3))
         with torch.cuda.device(self.device):

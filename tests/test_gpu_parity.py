@@ -293,3 +293,46 @@ def test_full_size_ddpm1000_b64_properties(engine):
     poses, trans = engine.decode(a)
     assert torch.isfinite(poses).all() and poses.shape == (B, 300, 55, 3)
     assert poses.abs().max().item() <= 3.1416 + 1e-3          # axis-angle magnitude is an angle in [0, pi]
+
+
+def test_empty_batch(engine):
+    """bsz = 0: the reference's modules return empty tensors for an empty batch; nothing is launched here."""
+    z = torch.empty(0, 256)
+    n0 = engine.launch_count()
+    out = engine.diffusion_backward(torch.empty(0, 128), z, z, z, n_steps=50, want_latents=True, want_feats=True)
+    assert tuple(out["poses"].shape) == (0, 300, 55, 3) and tuple(out["trans"].shape) == (0, 300, 3)
+    assert tuple(out["latents"].shape) == (0, 128) and tuple(out["feats"].shape) == (0, 300, 333)
+    assert out["poses"].device.type == "cuda" and out["poses"].dtype == torch.float32
+    assert tuple(engine.denoise(torch.empty(0, 128), z, None, None).shape) == (0, 128)
+    poses, trans = engine.decode(torch.empty(0, 128))
+    assert tuple(poses.shape) == (0, 300, 55, 3) and tuple(trans.shape) == (0, 300, 3)
+    mu, logvar = engine.encode(torch.empty(0, 300, 333))
+    assert tuple(mu.shape) == (0, 128) and tuple(logvar.shape) == (0, 128)
+    host = engine.diffusion_backward_host(torch.empty(0, 128), z, z, z, n_steps=50)
+    assert tuple(host["poses"].shape) == (0, 300, 55, 3) and host["poses"].device.type == "cpu"
+    assert engine.launch_count() == n0
+
+
+def test_wide_rows_layout_matches(engine, synthetic_weights, monkeypatch):
+    """The WIDE layout of the 2-clip kernel (AMUSE_WIDE_ROWS=1, a tuning hook read in amuse_create: 10-row GEMM
+    warps over 1/8 of K, partials parked in the idle exchange buffer) computes the same sampler as the default
+    layout: both against the oracle, on batch sizes with full and half-filled clusters and a 4-token ablation."""
+    from amuse_b200.engine import Engine
+    monkeypatch.setenv("AMUSE_WIDE_ROWS", "1")
+    wide = Engine("cuda:0")
+    monkeypatch.delenv("AMUSE_WIDE_ROWS")
+    try:
+        wide.load_state_dict("denoiser", synthetic_weights["denoiser"])
+        wide.finalize()
+        for B, sty in ((64, True), (35, False)):
+            g = torch.Generator().manual_seed(77 + B)
+            l0, con, emo = torch.randn(B, 128, generator=g), torch.randn(B, 256, generator=g), torch.randn(B, 256, generator=g)
+            zs = torch.randn(B, 256, generator=g) if sty else None
+            ref = R.sample_latents(synthetic_weights["denoiser"], l0, con, emo, zs, 10, "ddim")
+            a = wide.denoise(l0, con, emo, zs, n_steps=10, sampler="ddim").cpu()
+            b = engine.denoise(l0, con, emo, zs, n_steps=10, sampler="ddim").cpu()
+            ea, eb = (a - ref).abs().max().item(), (b - ref).abs().max().item()
+            print(f"[parity] wide-rows layout B={B}: wide max|d|={ea:.3e} default max|d|={eb:.3e}")
+            assert ea < 1e-4 and eb < 1e-4
+    finally:
+        wide.close()
