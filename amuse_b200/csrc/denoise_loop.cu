@@ -106,6 +106,32 @@ __device__ __forceinline__ const float* wp_acquire(const Smem& s, const WPipe& w
   mbar_wait(s.wbar(w.g & 1), (w.g >> 1) & 1);
   return s.wbuf(w.g & 1);
 }
+// Pre-waited tiles.  An mbarrier try_wait costs ~100 cycles even when the tile landed long ago (measured: 117..278
+// cycles between the end of a stage and the first GEMM instruction of the next), and every GEMM stage used to start
+// with one in all 10 warps.  Warp 9 (no GEMM role; its lane 0 issues the TMA) instead observes the completed phase
+// at a point where it would idle anyway, always before a __syncthreads() that precedes the stage, and the stage
+// starts without touching the mbarrier: the barrier orders warp 9's observation before every other warp's reads of
+// the tile.  Two placements, selected at compile time (both pass the full GPU suite; measured on one box, B = 64,
+// against 62.5 us/step with the all-thread wait):
+//   default                  while warps 0..7 run the GEMM of tile g, warp 9 waits for tile g+1 (issued a whole
+//                            stage earlier): covers every tile                                       61.3 us/step
+//   AMUSE_PREWAIT_IDLE_SITES under the exchange wait of the previous stage / during the attention stage; the FFN2
+//                            tile, which follows a stage without idle time, keeps the all-thread wait 62.0 us/step
+#ifdef AMUSE_PREWAIT_IDLE_SITES
+constexpr bool kPrewaitInGemm = false;
+#else
+constexpr bool kPrewaitInGemm = true;
+#endif
+__device__ __forceinline__ void wp_prewait(const Smem& s, const WPipe& w, uint32_t ahead) {
+  const uint32_t n = w.g + ahead;
+  if (n < w.total) mbar_wait(s.wbar(n & 1), (n >> 1) & 1);
+}
+__device__ __forceinline__ const float* wp_acquire_prewaited(const Smem& s, const WPipe& w) { return s.wbuf(w.g & 1); }
+// the FFN2 tile: pre-waited only by the in-GEMM placement
+__device__ __forceinline__ const float* wp_acquire_ffn2(const Smem& s, const WPipe& w) {
+  return kPrewaitInGemm ? wp_acquire_prewaited(s, w) : wp_acquire(s, w);
+}
+constexpr int kIssuerWarp = 9;
 // Call after a __syncthreads() that follows the last read of tile g: hands the buffer back
 // to the TMA engine for tile g+2.  Issued by one lane of warp 9, which has no GEMM role (measured
 // earlier: with thread 0 issuing, warp 0's epilogue was 700 cycles late in every stage).  No proxy
@@ -405,6 +431,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   }
   uint32_t xe = 0;   // running index of the DSMEM exchange (selects receive buffer + mbarrier phase)
   __syncthreads();
+  if (warp == kIssuerWarp) wp_prewait(s, wp, 0);   // tile 0 of step 0 (ordered by the cluster barrier below)
   cluster_sync_all();   // every CTA of the cluster is resident, zero-filled and has its mbarriers
                         // initialised before any peer stores into its shared memory
 
@@ -472,11 +499,15 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   // A lambda so that the three users (skip fusion, out_proj, FFN2) share one source form.
   auto exchange_epilogue = [&](const float* bias, const float* resid, const float* lnp, float* dst2, int prof_slot,
                                bool do_prof) {
+    Row4 v;
     if (own0) {
-      Row4 v = gather_row(row0);
+      v = gather_row(row0);
       send_row(s, xe, rank, row0, lane, v);
       v = add4(v, ld_row4(bias, lane));
       if (resid) v = add4(v, ld_row4(resid + row0 * 128, lane));
+    }
+    if (!kPrewaitInGemm && warp == kIssuerWarp) wp_prewait(s, wp, 0);   // next stage's tile, under the exchange wait
+    if (own0) {
       if (prof_slot >= 0 && prof_slot < 12 && do_prof && tid == 0) p.prof[prof_slot + 100] = clock64();   // layer 0 only
       exchange_wait(s, xe);
       if (prof_slot >= 0 && do_prof && tid == 0) p.prof[prof_slot] = clock64();
@@ -504,6 +535,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       layernorm1(v, lnp, lane);
       st_row4(Xs + arow * 128, lane, v);
     }
+    else if (!kPrewaitInGemm && warp == kIssuerWarp) wp_prewait(s, wp, 0);
     ++xe;
     __syncthreads();
   };
@@ -547,12 +579,14 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       // tried to keep the loop inside the 32 KB instruction cache: it was 7% slower overall).
       // =============== output blocks: x = Linear(256->128)(cat(x, xs.pop())), K-split 64 per CTA
       if (layer >= 5) {
-        const float* wt = wp_acquire(s, wp);
+        const float* wt = wp_acquire_prewaited(s, wp);
         exchange_arm<RT>(s, xe, tid);
         copy_params(par_tail, wt + 64 * 128, 128, tid);
         // my K slice of cat(x, skip): ranks 0,1 -> x[:, 64*rank ..], ranks 2,3 -> skip[:, 64*(rank-2) ..]
         const float* src = (rank < 2) ? (Xs + rank * 64) : (SK + (8 - layer) * kRMax * 128 + (rank - 2) * 64);
-        if (gw) {
+        if (!gw) {
+          if (kPrewaitInGemm && warp == kIssuerWarp) wp_prewait(s, wp, 1);   // next tile, while the GEMM runs
+        } else {
           float acc[NRW][4];
           gemm_rows<NRW, 128, 4, (64 / KS) / 4>(src + (rb * 5) * 128 + ks * (64 / KS), 128,
                                                 wt + (ks * (32 / KS)) * 256 + lane * 2, acc);
@@ -566,10 +600,12 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
 
       // =============== QKV of my head (cross_attention.py:264-266, nn.MultiheadAttention in_proj)
       {
-        const float* wt = wp_acquire(s, wp);
+        const float* wt = wp_acquire_prewaited(s, wp);
         AMUSE_FINE(120);
         copy_params(par_bqkv, wt + 128 * 96, 96, tid);
-        if (gw) {
+        if (!gw) {
+          if (kPrewaitInGemm && warp == kIssuerWarp) wp_prewait(s, wp, 1);   // next tile, while the GEMM runs
+        } else {
           float acc[NRW][3];
           gemm_rows<NRW, 96, 3, (128 / KS) / 4>(Xs + (rb * 5) * 128 + ks * (128 / KS), 128,
                                                 wt + (ks * (64 / KS)) * 192 + lane * 2, acc);
@@ -656,16 +692,19 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
               make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
         }
       }
+      else if (!kPrewaitInGemm && warp == kIssuerWarp) wp_prewait(s, wp, 0);   // out_proj tile, during the attention
       __syncthreads();
       AMUSE_PROF(2 + layer * 10 + 2);
 
       if (PRUNE && layer == kLayers - 1) {
         // =============== last layer, token 0 of every clip only (see PRUNE above)
         {   // out_proj
-          const float* wt = wp_acquire(s, wp);
+          const float* wt = wp_acquire_prewaited(s, wp);
           exchange_arm<RB>(s, xe, tid);
           copy_params(par_tail, wt + 32 * 128, kTileTail, tid);
-          if (gw) {
+          if (!gw) {
+          if (kPrewaitInGemm && warp == kIssuerWarp) wp_prewait(s, wp, 1);   // next tile, while the GEMM runs
+        } else {
             float acc[RB][4];
             gemm_rows<RB, 128, 4, 1>(Oh + warp * 4, T * kOhLd, wt + (warp * 2) * 256 + lane * 2, acc);
             park_rows<RB>(RED, warp, lane, acc);
@@ -676,9 +715,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         }
         AMUSE_PROF(2 + layer * 10 + 4);
         {   // FFN1 + erf-GELU
-          const float* wt = wp_acquire(s, wp);
+          const float* wt = wp_acquire_prewaited(s, wp);
           copy_params(par_tail, wt + 128 * 128, 128, tid);
-          if (gw) {
+          if (!gw) {
+          if (kPrewaitInGemm && warp == kIssuerWarp) wp_prewait(s, wp, 1);   // next tile, while the GEMM runs
+        } else {
             float acc[RB][4];
             gemm_rows<RB, 128, 4, 4>(Xs + warp * 16, T * 128, wt + (warp * 8) * 256 + lane * 2, acc);
             park_rows<RB>(RED, warp, lane, acc);
@@ -695,10 +736,12 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         }
         AMUSE_PROF(2 + layer * 10 + 5);
         {   // FFN2
-          const float* wt = wp_acquire(s, wp);
+          const float* wt = wp_acquire_ffn2(s, wp);
           exchange_arm<RB>(s, xe, tid);
           copy_params(par_tail, wt + 128 * 128, kTileTail, tid);
-          if (gw) {
+          if (!gw) {
+          if (kPrewaitInGemm && warp == kIssuerWarp) wp_prewait(s, wp, 1);   // next tile, while the GEMM runs
+        } else {
             float acc[RB][4];
             gemm_rows<RB, 128, 4, 4>(Hs + warp * 16, T * 128, wt + (warp * 8) * 256 + lane * 2, acc);
             park_rows<RB>(RED, warp, lane, acc);
@@ -712,11 +755,13 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       }
       // =============== out_proj, K-split by head -> st.async partial exchange -> sum + LN1
       {
-        const float* wt = wp_acquire(s, wp);
+        const float* wt = wp_acquire_prewaited(s, wp);
         AMUSE_FINE(124);
         exchange_arm<RT>(s, xe, tid);
         copy_params(par_tail, wt + 32 * 128, kTileTail, tid);
-        if (gw) {
+        if (!gw) {
+          if (kPrewaitInGemm && warp == kIssuerWarp) wp_prewait(s, wp, 1);   // next tile, while the GEMM runs
+        } else {
           float acc[NRW][4];
           gemm_rows<NRW, 128, 4, (32 / KS) / 4>(Oh + (rb * 5) * kOhLd + ks * (32 / KS), kOhLd,
                                                 wt + (ks * (16 / KS)) * 256 + lane * 2, acc);
@@ -732,10 +777,12 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
 
       // =============== FFN1: my 128 hidden units, erf-GELU
       {
-        const float* wt = wp_acquire(s, wp);
+        const float* wt = wp_acquire_prewaited(s, wp);
         AMUSE_FINE(112);
         copy_params(par_tail, wt + 128 * 128, 128, tid);
-        if (gw) {
+        if (!gw) {
+          if (kPrewaitInGemm && warp == kIssuerWarp) wp_prewait(s, wp, 1);   // next tile, while the GEMM runs
+        } else {
           float acc[NRW][4];
           gemm_rows<NRW, 128, 4, (128 / KS) / 4>(Xs + (rb * 5) * 128 + ks * (128 / KS), 128,
                                                  wt + (ks * (64 / KS)) * 256 + lane * 2, acc);
@@ -758,11 +805,13 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
 
       // =============== FFN2, K-split over my 128 hidden units -> exchange -> sum + LN2
       {
-        const float* wt = wp_acquire(s, wp);
+        const float* wt = wp_acquire_ffn2(s, wp);
         AMUSE_FINE(116);
         exchange_arm<RT>(s, xe, tid);
         copy_params(par_tail, wt + 128 * 128, kTileTail, tid);
-        if (gw) {
+        if (!gw) {
+          if (kPrewaitInGemm && warp == kIssuerWarp) wp_prewait(s, wp, 1);   // next tile, while the GEMM runs
+        } else {
           float acc[NRW][4];
           gemm_rows<NRW, 128, 4, (128 / KS) / 4>(Hs + (rb * 5) * 128 + ks * (128 / KS), 128,
                                                  wt + (ks * (64 / KS)) * 256 + lane * 2, acc);

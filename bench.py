@@ -381,6 +381,11 @@ def run_ours(args, rank, world, local_rank):
     peak_tf, hbm_gbs, peak_kind = load_peaks()
     flops_loop = B * N_STEPS * FLOP_DENOISE_PER_CLIP_STEP          # per launch of denoise_loop_kernel
     ach_tf = flops_loop / (t_loop / K) / 1e12
+    # The pipe this fp32 kernel actually runs on: FFMA2 issues every 2.75 cycles per SM sub-partition (measured,
+    # scripts/ubench.cu) = 93.1 FMA/clk/SM, on the 4 SMs of every 2-clip cluster, at the SM clock sampled under load.
+    sms_used = 4 * ((B + 1) // 2)
+    sm_hz = float((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+    fma_peak_tf = 2 * 93.1 * sms_used * sm_hz / 1e12
     h2d = sum(t.numel() * 4 for t in h)
     d2h = out_poses.numel() * 4 + out_trans.numel() * 4
 
@@ -443,6 +448,9 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "denoise_loop_kernel", "achieved": ach_tf, "peak": peak_tf,
                      "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": DENOISE_LOOP_DRAM_BYTES,
+                     "fp32_fma": {"achieved": ach_tf, "peak": fma_peak_tf, "unit": "TFLOP/s", "frac": ach_tf / fma_peak_tf,
+                                  "sms_used": sms_used,
+                                  "note": "measured FFMA2 issue rate (93.1 FMA/clk/SM) x SMs holding a cluster x sampled SM clock"},
                      "note": f"algorithmic 19.219 MFLOP x {B} clips x {N_STEPS} steps per launch; peak = {peak_kind} dense bf16 "
                              "(sustained); the kernel computes in fp32 FFMA and is dependency-latency bound at 5 rows/clip"},
         "cpu_baseline": {"value": cpu_value, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
