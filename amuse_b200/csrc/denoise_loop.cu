@@ -623,6 +623,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         __syncthreads();
         AMUSE_FINE(122);
         wp_release(s, wp, tid);
+        // (The same sums as 24 lanes x float4 instead of 32 lanes x 3 scalars were measured slower: 61.1 vs 60.6 us/step.)
         if (own0) {
           float q = par_bqkv[lane], k = par_bqkv[32 + lane], v = par_bqkv[64 + lane];
 #pragma unroll
