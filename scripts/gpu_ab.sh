@@ -1,11 +1,10 @@
 #!/bin/bash
-# GPU box: parity tests with the product library, then timing + stage profile of it and of each
-# variant library given as argument (names as built by scripts/build_variant.sh)
+# GPU box: product vs one variant library -- timing (2 clips and 1 clip per cluster) and the full -m gpu suite on both
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q -s > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
-grep -E "parity\] (ddim|ddpm|backward|live ddim10 B=64|train)|passed|failed|Error|error" gpurun_out/pytest_gpu.log | tail -24
-timeout 300 python scripts/quick_bench.py 64 > gpurun_out/quick64.log 2>&1; echo "--- product rc=$?"; tail -17 gpurun_out/quick64.log
-for v in "$@"; do
-  AMUSE_B200_LIB=amuse_b200/lib/libamuse_b200_$v.so timeout 300 python scripts/quick_bench.py 64 > gpurun_out/quick64_$v.log 2>&1
-  echo "--- variant $v rc=$?"; tail -17 gpurun_out/quick64_$v.log
+v=$1
+for b in 64 32; do
+  timeout 200 python scripts/quick_bench.py $b > gpurun_out/quick$b.log 2>&1; echo "--- product B=$b rc=$?"; grep -E "^denoise|step cycles" gpurun_out/quick$b.log
+  AMUSE_B200_LIB=amuse_b200/lib/libamuse_b200_$v.so timeout 200 python scripts/quick_bench.py $b > gpurun_out/quick${b}_$v.log 2>&1; echo "--- $v B=$b rc=$?"; grep -E "^denoise|step cycles" gpurun_out/quick${b}_$v.log
 done
+AMUSE_B200_LIB=amuse_b200/lib/libamuse_b200_$v.so timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$v.log 2>&1; echo "pytest $v rc=$?"; tail -1 gpurun_out/pytest_$v.log
+timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest product rc=$?"; tail -1 gpurun_out/pytest_gpu.log
