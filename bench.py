@@ -42,7 +42,7 @@ AUDIO_SAMPLES = 160000                     # 10 s at 16 kHz
 # dram__bytes_read.sum + dram__bytes_write.sum of one denoise_loop_kernel launch (ncu --set full,
 # profiles/r01_denoise_loop_full.txt): the 8.77 MB of repacked weights are read from HBM once per launch and
 # served from L2 for every later step; activations never leave shared memory (0 B written).
-DENOISE_LOOP_DRAM_BYTES = 8045312
+DENOISE_LOOP_DRAM_BYTES = 8049152
 METRIC = "SMPL-X pose frames/sec over full DDPM sampling (10 s clip, batch 64)"
 
 
