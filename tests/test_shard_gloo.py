@@ -4,6 +4,7 @@ inputs) because the CUDA engine needs a GPU; the sharding / collective plumbing 
 import os
 import socket
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -35,8 +36,9 @@ def _worker(rank, world, port, n_global, ret):
     dist.destroy_process_group()
 
 
-def test_broadcast_shard_gather_two_ranks():
-    world, n_global = 2, 7                                  # ragged: 4 + 3 clips
+@pytest.mark.parametrize("n_global", [7, 1])               # ragged: 4 + 3 clips; 1 + 0 clips (an empty shard)
+def test_broadcast_shard_gather_two_ranks(n_global):
+    world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
     port = _free_port()
