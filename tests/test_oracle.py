@@ -183,3 +183,41 @@ def test_ast_restatement_matches_hf_transformers():
             got = A.ast_branch(sd, prefix, fb)
         assert got.shape == (2, 256)
         assert float((got - want).abs().max()) < 2e-5 * max(1.0, float(want.abs().max()))
+
+
+def test_scheduler_tables_against_published_formulas():
+    """The restated scheduler tables against the closed forms of the papers, evaluated independently in float64
+    numpy: scaled-linear betas (latent-diffusion convention), DDIM eq. 12 with eta = 0 (Song et al.),
+    the DDPM posterior mean / fixed-small variance (Ho et al. eq. 6-7).  diffusers itself is not installable here
+    (parity unpinned); this pins the restatement to the published algorithm instead."""
+    betas = np.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=np.float64) ** 2
+    ac = np.cumprod(1.0 - betas)
+    assert np.allclose(R.alphas_cumprod().double().numpy(), ac, rtol=2e-6, atol=0)
+    # DDIM, 50 steps, leading-offset timesteps t = 1 + 20 i, final alpha = alphas_cumprod[0]
+    plan = R.ddim_coeffs(50)
+    ts = np.array(plan["timesteps"])
+    assert np.array_equal(ts, (np.arange(50) * 20)[::-1] + 1)
+    a, ap = ac[ts], np.where(ts - 20 >= 0, ac[np.maximum(ts - 20, 0)], ac[0])
+    want = np.stack([a ** 0.5, (1 - a) ** 0.5, ap ** 0.5, (1 - ap) ** 0.5, np.zeros(50)], 1)
+    # fp32 library order: 1 - a is rounded in fp32 before the sqrt, a relative 4e-5 on sqrt(1 - a) where a -> 1
+    assert np.allclose(plan["coef"].double().numpy(), want, rtol=3e-6, atol=3e-6)
+    # DDPM, 1000 steps: x' = c0 x0 + cx x + sigma z with the posterior coefficients of Ho et al.
+    plan = R.ddpm_coeffs(1000)
+    ts = np.array(plan["timesteps"])
+    assert np.array_equal(ts, np.arange(1000)[::-1])
+    a, ap = ac[ts], np.where(ts > 0, ac[np.maximum(ts - 1, 0)], 1.0)
+    beta_t = 1.0 - a / ap
+    c0 = ap ** 0.5 * beta_t / (1 - a)
+    cx = (a / ap) ** 0.5 * (1 - ap) / (1 - a)
+    sigma = np.where(ts > 0, np.sqrt(np.maximum((1 - ap) / (1 - a) * beta_t, 1e-20)), 0.0)
+    want = np.stack([a ** 0.5, (1 - a) ** 0.5, c0, cx, sigma], 1)
+    got = plan["coef"].double().numpy()
+    assert np.allclose(got[:, :2], want[:, :2], rtol=3e-6, atol=3e-6)
+    assert np.allclose(got[:, 2:], want[:, 2:], rtol=3e-4, atol=3e-6)   # beta_t = 1 - a/a' and 1 - a cancel in fp32
+    # one full step of each sampler against the formula applied directly
+    g = torch.Generator().manual_seed(3)
+    x, e, z = (torch.randn(4, 128, generator=g, dtype=torch.float64) for _ in range(3))
+    i = 500
+    got = R.scheduler_step(plan, i, x, e, z).numpy()
+    x0 = (x.numpy() - (1 - a[i]) ** 0.5 * e.numpy()) / a[i] ** 0.5
+    assert np.allclose(got, c0[i] * x0 + cx[i] * x.numpy() + sigma[i] * z.numpy(), rtol=1e-5, atol=1e-6)
