@@ -19,7 +19,7 @@
 
 using namespace amuse;
 
-constexpr int kCl = 4, kThr = 320, kRows = 10;
+constexpr int kThr = 320, kRows = 10;   // kRows = buffer geometry; NROWS of them are exchanged
 
 __device__ __forceinline__ void st_async_v2(uint32_t dst, float2 v, uint32_t mbar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(dst),
@@ -41,7 +41,8 @@ __device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster, uint32_t src_cta,
 // smem: stage [2][10][128] | recv [2][3][10][128] | bars[2].  The staging buffer alternates like the receive
 // buffers: an outgoing bulk copy of round xe has been consumed by every peer before any of them can send round
 // xe+1, which this CTA waits for before it writes the staging buffer of round xe+2.
-template <int MODE, int ROWB>
+// kCl = cluster size (4 = today, 2 = the one-clip-per-2-CTA-cluster candidate), NROWS = rows per exchange (10 / 5)
+template <int MODE, int ROWB, int kCl = 4, int NROWS = kRows>
 __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThr, 1) k_exchange(float* sink, long long* cyc, int reps) {
   extern __shared__ __align__(128) float sm[];
   float* recv = sm + 2 * kRows * 128;
@@ -66,12 +67,13 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThr, 1) k_exchang
     uint64_t* bar = bars + (xe & 1);
     __syncthreads();
     const long long t0 = clock64();
-    if (tid == 0) mbar_arrive_expect_tx(bar, 3u * kRows * ROWB);
+    if (tid == 0) mbar_arrive_expect_tx(bar, static_cast<uint32_t>(kCl - 1) * NROWS * ROWB);
     const int row = warp;   // 10 warps, one row each
+    const bool owner = row < NROWS;
     // the value a row owner would have after its gather (depends on the previous round so nothing is hoisted)
     const float base = acc * 1e-30f + static_cast<float>(xe + row);
     if (MODE == 0) {
-      if (lane * 2 < RF) {
+      if (owner && lane * 2 < RF) {
 #pragma unroll
         for (uint32_t d = 1; d < kCl; ++d) {
           const uint32_t peer = (rank + d) & (kCl - 1), slot = (rank < peer) ? rank : rank - 1;
@@ -82,7 +84,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThr, 1) k_exchang
         }
       }
     } else if (MODE == 1) {
-      if (lane * 4 < RF) {
+      if (owner && lane * 4 < RF) {
 #pragma unroll
         for (uint32_t d = 1; d < kCl; ++d) {
           const uint32_t peer = (rank + d) & (kCl - 1), slot = (rank < peer) ? rank : rank - 1;
@@ -93,11 +95,11 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThr, 1) k_exchang
       }
     } else {
       // write the row into the local staging buffer, make it visible to the async proxy
-      if (lane * 4 < RF) *reinterpret_cast<float4*>(stage + row * RF + 4 * lane) = make_float4(base, base + 1.f, base + 2.f, base + 3.f);
+      if (owner && lane * 4 < RF) *reinterpret_cast<float4*>(stage + row * RF + 4 * lane) = make_float4(base, base + 1.f, base + 2.f, base + 3.f);
       fence_proxy_async();
       if (MODE == 2) {
         __syncwarp();
-        if (lane == 0) {
+        if (owner && lane == 0) {
 #pragma unroll
           for (uint32_t d = 1; d < kCl; ++d) {
             const uint32_t peer = (rank + d) & (kCl - 1), slot = (rank < peer) ? rank : rank - 1;
@@ -106,10 +108,10 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThr, 1) k_exchang
         }
       } else {
         __syncthreads();
-        if (tid < 3) {
+        if (tid < kCl - 1) {
           const uint32_t d = tid + 1;
           const uint32_t peer = (rank + d) & (kCl - 1), slot = (rank < peer) ? rank : rank - 1;
-          bulk_s2c(map_to_rank(rb + slot * kRows * RF, peer), smem_u32(stage), kRows * ROWB, map_to_rank(bar, peer));
+          bulk_s2c(map_to_rank(rb + slot * kRows * RF, peer), smem_u32(stage), NROWS * ROWB, map_to_rank(bar, peer));
         }
       }
     }
@@ -117,9 +119,9 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThr, 1) k_exchang
     const long long t1 = clock64();
     t_sum += t1 - t0;
     // consume what arrived (the kernel's add_peers): the next round's data depends on it
-    if (lane * 2 < RF) {
+    if (owner && lane * 2 < RF) {
 #pragma unroll
-      for (int q = 0; q < 3; ++q) acc += rb[(q * kRows + row) * (MODE >= 2 ? RF : 128) + 2 * lane];
+      for (int q = 0; q < kCl - 1; ++q) acc += rb[(q * kRows + row) * (MODE >= 2 ? RF : 128) + 2 * lane];
     }
   }
   if (blockIdx.x == 0 && tid == 0) cyc[0] = t_sum;
@@ -127,18 +129,18 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThr, 1) k_exchang
   cluster_sync_all();
 }
 
-template <int MODE, int ROWB>
+template <int MODE, int ROWB, int kCl = 4, int NROWS = kRows>
 static void run(const char* name, float* sink, long long* cyc) {
   const int reps = 2000;
   const size_t smem = (kRows * 128 * 8) * sizeof(float) + 64;
-  cudaFuncSetAttribute(k_exchange<MODE, ROWB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  for (int grid : {4, 128}) {
-    k_exchange<MODE, ROWB><<<grid, kThr, smem>>>(sink, cyc, 200);
-    k_exchange<MODE, ROWB><<<grid, kThr, smem>>>(sink, cyc, reps);
+  cudaFuncSetAttribute(k_exchange<MODE, ROWB, kCl, NROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  for (int grid : {kCl, 128}) {
+    k_exchange<MODE, ROWB, kCl, NROWS><<<grid, kThr, smem>>>(sink, cyc, 200);
+    k_exchange<MODE, ROWB, kCl, NROWS><<<grid, kThr, smem>>>(sink, cyc, reps);
     cudaError_t e = cudaDeviceSynchronize();
     long long h = 0;
     cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
-    printf("%-28s row %3d B  (%5d B out/CTA)  clusters %2d : %7.1f cycles / exchange   [%s]\n", name, ROWB, 3 * kRows * ROWB,
+    printf("%-28s row %3d B  (%5d B out/CTA)  clusters %2d : %7.1f cycles / exchange   [%s]\n", name, ROWB, (kCl - 1) * NROWS * ROWB,
            grid / kCl, static_cast<double>(h) / reps, cudaGetErrorString(e));
   }
 }
@@ -159,5 +161,9 @@ int main() {
   run<3, 512>("bulk per peer (+syncthreads)", sink, cyc);
   run<3, 256>("bulk per peer (+syncthreads)", sink, cyc);
   run<3, 128>("bulk per peer (+syncthreads)", sink, cyc);
+  // the 2-CTA-cluster candidate of DESIGN.md section 6.1a: one peer, 5 rows (one clip)
+  run<0, 512, 2, 5>("2-CTA cluster, 5 rows, v2", sink, cyc);
+  run<1, 512, 2, 5>("2-CTA cluster, 5 rows, v4", sink, cyc);
+  run<0, 512, 4, 5>("4-CTA cluster, 5 rows, v2", sink, cyc);
   return 0;
 }
