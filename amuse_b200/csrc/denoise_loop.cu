@@ -329,6 +329,13 @@ __device__ __forceinline__ void layernorm1(Row4& v, const float* lnp, int lane) 
 // The bias / LayerNorm vectors of a stage are copied out of the weight tile so that the ring slot can be handed
 // back to the TMA engine before the epilogue runs.  All 10 warps copy: leaving it to the two warps without a
 // GEMM role was measured 3% slower per step (64.5 vs 62.5 us), their 6 dependent LDS/STS rounds end after the GEMM.
+// AMUSE_COPY_AFTER_GEMM (untested candidate): issue the copy after the GEMM call instead of
+// before it, so that its LDS -> STS round trip is not in front of every warp's first GEMM load.
+#ifdef AMUSE_COPY_AFTER_GEMM
+constexpr bool kCopyAfterGemm = true;
+#else
+constexpr bool kCopyAfterGemm = false;
+#endif
 __device__ __forceinline__ void copy_params(float* dst, const float* src, int n, int tid) {
   for (int i = tid; i < n; i += kThreads) dst[i] = src[i];
 }
@@ -583,7 +590,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       if (layer >= 5) {
         const float* wt = wp_acquire_prewaited(s, wp);
         exchange_arm<RT>(s, xe, tid);
-        copy_params(par_tail, wt + 64 * 128, 128, tid);
+        if (!kCopyAfterGemm) copy_params(par_tail, wt + 64 * 128, 128, tid);
         // my K slice of cat(x, skip): ranks 0,1 -> x[:, 64*rank ..], ranks 2,3 -> skip[:, 64*(rank-2) ..]
         const float* src = (rank < 2) ? (Xs + rank * 64) : (SK + (8 - layer) * kRMax * 128 + (rank - 2) * 64);
         if (!gw) {
@@ -594,6 +601,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
                                                 wt + (ks * (32 / KS)) * 256 + lane * 2, acc);
           park_tile(acc);
         }
+        if (kCopyAfterGemm) copy_params(par_tail, wt + 64 * 128, 128, tid);
         __syncthreads();
         wp_release(s, wp, tid);
         exchange_epilogue(par_tail, nullptr, nullptr, nullptr, -1, do_prof);
@@ -604,7 +612,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       {
         const float* wt = wp_acquire_prewaited(s, wp);
         AMUSE_FINE(120);
-        copy_params(par_bqkv, wt + 128 * 96, 96, tid);
+        if (!kCopyAfterGemm) copy_params(par_bqkv, wt + 128 * 96, 96, tid);
         if (!gw) {
           if (kPrewaitInGemm && warp == kIssuerWarp) wp_prewait(s, wp, 1);   // next tile, while the GEMM runs
         } else {
@@ -620,6 +628,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
             dst[i * 96 + 64] = acc[i][2];
           }
         }
+        if (kCopyAfterGemm) copy_params(par_bqkv, wt + 128 * 96, 96, tid);
         __syncthreads();
         AMUSE_FINE(122);
         wp_release(s, wp, tid);
@@ -704,7 +713,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         {   // out_proj
           const float* wt = wp_acquire_prewaited(s, wp);
           exchange_arm<RB>(s, xe, tid);
-          copy_params(par_tail, wt + 32 * 128, kTileTail, tid);
+          if (!kCopyAfterGemm) copy_params(par_tail, wt + 32 * 128, kTileTail, tid);
           if (!gw) {
           if (kPrewaitInGemm && warp == kIssuerWarp) wp_prewait(s, wp, 1);   // next tile, while the GEMM runs
         } else {
@@ -712,6 +721,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
             gemm_rows<RB, 128, 4, 1>(Oh + warp * 4, T * kOhLd, wt + (warp * 2) * 256 + lane * 2, acc);
             park_rows<RB>(RED, warp, lane, acc);
           }
+          if (kCopyAfterGemm) copy_params(par_tail, wt + 32 * 128, kTileTail, tid);
           __syncthreads();
           wp_release(s, wp, tid);
           exchange_epilogue_pruned(par_tail, par_tail + 128, 2 + layer * 10 + 3, do_prof);
@@ -719,7 +729,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         AMUSE_PROF(2 + layer * 10 + 4);
         {   // FFN1 + erf-GELU
           const float* wt = wp_acquire_prewaited(s, wp);
-          copy_params(par_tail, wt + 128 * 128, 128, tid);
+          if (!kCopyAfterGemm) copy_params(par_tail, wt + 128 * 128, 128, tid);
           if (!gw) {
           if (kPrewaitInGemm && warp == kIssuerWarp) wp_prewait(s, wp, 1);   // next tile, while the GEMM runs
         } else {
@@ -727,6 +737,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
             gemm_rows<RB, 128, 4, 4>(Xs + warp * 16, T * 128, wt + (warp * 8) * 256 + lane * 2, acc);
             park_rows<RB>(RED, warp, lane, acc);
           }
+          if (kCopyAfterGemm) copy_params(par_tail, wt + 128 * 128, 128, tid);
           __syncthreads();
           wp_release(s, wp, tid);
           if (warp < RB) {
@@ -741,7 +752,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         {   // FFN2
           const float* wt = wp_acquire_ffn2(s, wp);
           exchange_arm<RB>(s, xe, tid);
-          copy_params(par_tail, wt + 128 * 128, kTileTail, tid);
+          if (!kCopyAfterGemm) copy_params(par_tail, wt + 128 * 128, kTileTail, tid);
           if (!gw) {
           if (kPrewaitInGemm && warp == kIssuerWarp) wp_prewait(s, wp, 1);   // next tile, while the GEMM runs
         } else {
@@ -749,6 +760,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
             gemm_rows<RB, 128, 4, 4>(Hs + warp * 16, T * 128, wt + (warp * 8) * 256 + lane * 2, acc);
             park_rows<RB>(RED, warp, lane, acc);
           }
+          if (kCopyAfterGemm) copy_params(par_tail, wt + 128 * 128, kTileTail, tid);
           __syncthreads();
           wp_release(s, wp, tid);
           exchange_epilogue_pruned(par_tail, par_tail + 128, 2 + layer * 10 + 6, do_prof);
@@ -761,7 +773,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         const float* wt = wp_acquire_prewaited(s, wp);
         AMUSE_FINE(124);
         exchange_arm<RT>(s, xe, tid);
-        copy_params(par_tail, wt + 32 * 128, kTileTail, tid);
+        if (!kCopyAfterGemm) copy_params(par_tail, wt + 32 * 128, kTileTail, tid);
         if (!gw) {
           if (kPrewaitInGemm && warp == kIssuerWarp) wp_prewait(s, wp, 1);   // next tile, while the GEMM runs
         } else {
@@ -771,6 +783,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
           AMUSE_FINE(125);
           park_tile(acc);
         }
+        if (kCopyAfterGemm) copy_params(par_tail, wt + 32 * 128, kTileTail, tid);
         __syncthreads();
         AMUSE_FINE(126);
         wp_release(s, wp, tid);
@@ -782,7 +795,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       {
         const float* wt = wp_acquire_prewaited(s, wp);
         AMUSE_FINE(112);
-        copy_params(par_tail, wt + 128 * 128, 128, tid);
+        if (!kCopyAfterGemm) copy_params(par_tail, wt + 128 * 128, 128, tid);
         if (!gw) {
           if (kPrewaitInGemm && warp == kIssuerWarp) wp_prewait(s, wp, 1);   // next tile, while the GEMM runs
         } else {
@@ -792,6 +805,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
           AMUSE_FINE(113);
           park_tile(acc);
         }
+        if (kCopyAfterGemm) copy_params(par_tail, wt + 128 * 128, 128, tid);
         __syncthreads();
         AMUSE_FINE(114);
         wp_release(s, wp, tid);
@@ -811,7 +825,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         const float* wt = wp_acquire_ffn2(s, wp);
         AMUSE_FINE(116);
         exchange_arm<RT>(s, xe, tid);
-        copy_params(par_tail, wt + 128 * 128, kTileTail, tid);
+        if (!kCopyAfterGemm) copy_params(par_tail, wt + 128 * 128, kTileTail, tid);
         if (!gw) {
           if (kPrewaitInGemm && warp == kIssuerWarp) wp_prewait(s, wp, 1);   // next tile, while the GEMM runs
         } else {
@@ -821,6 +835,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
           AMUSE_FINE(117);
           park_tile(acc);
         }
+        if (kCopyAfterGemm) copy_params(par_tail, wt + 128 * 128, kTileTail, tid);
         __syncthreads();
         AMUSE_FINE(118);
         wp_release(s, wp, tid);
