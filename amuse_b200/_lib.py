@@ -18,6 +18,7 @@ SYMBOLS = [
     "amuse_rot6d_to_axis_angle", "amuse_diffusion_backward", "amuse_diffusion_backward_host",
     "amuse_ast_features", "amuse_schedule", "amuse_launch_count", "amuse_profile_arm", "amuse_profile_read",
     "amuse_debug_tc_gemm", "amuse_debug_attn_profile", "amuse_debug_set_decode_plan", "amuse_fbank", "amuse_encode", "amuse_motion_to_feats",
+    "amuse_debug_philox_normals",
 ]
 
 AMUSE_OK = 0
@@ -60,12 +61,12 @@ def load() -> C.CDLL:
     lib.amuse_load_weights.argtypes = [p, C.c_char_p, p, C.POINTER(i64), i, i]
     lib.amuse_finalize_weights.argtypes = [p, p]
     lib.amuse_reserve.argtypes = [p, i, i]
-    lib.amuse_denoise.argtypes = [p, i, i, i, f, i, p, p, p, p, p, u64, p, p]
+    lib.amuse_denoise.argtypes = [p, i, i, i, f, i, p, p, p, p, p, u64, u64, p, p]
     lib.amuse_denoiser_eps.argtypes = [p, i, i, p, p, p, p, p, p]
     lib.amuse_decode.argtypes = [p, i, p, p, p, p, p]
     lib.amuse_rot6d_to_axis_angle.argtypes = [p, i64, p, p, p]
-    lib.amuse_diffusion_backward.argtypes = [p, i, i, i, f, i, p, p, p, p, p, u64, p, p, p, p, p]
-    lib.amuse_diffusion_backward_host.argtypes = [p, i, i, i, f, i, p, p, p, p, p, u64, p, p, p]
+    lib.amuse_diffusion_backward.argtypes = [p, i, i, i, f, i, p, p, p, p, p, u64, u64, p, p, p, p, p]
+    lib.amuse_diffusion_backward_host.argtypes = [p, i, i, i, f, i, p, p, p, p, p, u64, u64, p, p, p]
     lib.amuse_ast_features.argtypes = [p, i, p, p, p, p, p]
     lib.amuse_schedule.argtypes = [p, i, i, f, C.POINTER(C.c_int32), C.POINTER(f)]
     lib.amuse_launch_count.argtypes = [p]
@@ -75,6 +76,7 @@ def load() -> C.CDLL:
     lib.amuse_fbank.argtypes = [p, i, i, p, f, f, p, p]
     lib.amuse_debug_attn_profile.argtypes = [p, i, p, i]
     lib.amuse_debug_set_decode_plan.argtypes = [p, i, i]
+    lib.amuse_debug_philox_normals.argtypes = [p, u64, u64, i, i, p, p]
     lib.amuse_encode.argtypes = [p, i, p, p, p, p]
     lib.amuse_motion_to_feats.argtypes = [p, i64, p, p, p, p]
     lib.amuse_debug_tc_gemm.argtypes = [p, i, i, i, i, p, p, i, p, p, p, p, p, i, p, p]

@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "decode_kernels.cuh"
 #include "denoise_loop.cuh"
+#include "denoise_tc.cuh"
 #include "fbank_kernel.cuh"
 #include "small_kernels.cuh"
 #include "tc_gemm.cuh"
@@ -101,6 +102,7 @@ struct EncW {
 
 struct DenW {
   DevBuf blob, misc;
+  DevBuf blob2, vecs2;   // tensor-core loop kernel (denoise_tc.cu): fp16 hi/lo' weight stream + per-tile vectors
   // offsets into misc
   size_t freqs, w1t, b1, w2t, b2, condw[3], condb[3], pe, fnorm;
   bool ready = false;
@@ -129,6 +131,8 @@ struct amuse_ctx {
   bool dec_use_tc = true;        // decoder GEMMs on tcgen05 (3xTF32); false = fp32 FFMA kernels
   int prune_last = 1;            // denoise loop: last layer for token 0 only (AMUSE_PRUNE_LAST=0 disables; tuning hook)
   int wide_rows = 0;             // denoise loop: 10-row GEMM warps in 2-clip clusters (AMUSE_WIDE_ROWS=0/1; tuning hook)
+  bool den_ffma = false;         // denoise loop on the fp32 FFMA2 kernel (denoise_loop.cu) instead of the tcgen05 one
+                                 // (denoise_tc.cu): AMUSE_DENOISE_FFMA=1, A/B switch for measurements
   DevBuf h2d;   // staging for the *_host entry point
   DevBuf mel_t; // [257][128] mel filterbank weights (K-major)
   long long* d_prof = nullptr;
@@ -377,6 +381,84 @@ int pack_denoiser(amuse_ctx* ctx, cudaStream_t st) {
       }
     }
   }
+  // ---- the tensor-core loop kernel's streams (denoise_tc.cuh): per rank, tiles in consumption order, each tile the
+  //      fp16 hi / lo' planes of a [128 features x K] A operand in the producers' read order; + bias / LayerNorm vectors
+  std::vector<uint32_t> blob2(static_cast<size_t>(dn2::kCluster) * dn2::kRankVec4 * 4, 0u);
+  std::vector<float> vecs2(static_cast<size_t>(dn2::kCluster) * dn2::kRankVecFloats, 0.f);
+  {
+    auto put_tile = [](uint32_t* dst, int kind, auto&& Wfk) {   // Wfk(f, k): weight of output feature f, input feature k
+      const int K = dn2::tile_K(kind), quads = dn2::tile_quads(kind), units = dn2::tile_units(kind);
+      for (int u = 0; u < units; ++u)
+        for (int q = 0; q < quads; ++q)
+          for (int i = 0; i < 4; ++i)
+            for (int lane = 0; lane < 32; ++lane)
+              for (int w = 0; w < 4; ++w) {
+                const int col = 16 * u + 4 * i + w, f = q * 32 + lane;
+                const bool lo = col >= K / 2;
+                const int k0 = 2 * (lo ? col - K / 2 : col);
+                uint32_t word = 0;
+                for (int e = 0; e < 2; ++e) {
+                  uint16_t h, l;
+                  dn2::split_fp16(Wfk(f, k0 + e), h, l);
+                  word |= static_cast<uint32_t>(lo ? l : h) << (16 * e);
+                }
+                dst[((((static_cast<size_t>(u) * quads + q) * 4 + i) * 32) + lane) * 4 + w] = word;
+              }
+    };
+    for (int l = 0; l < 9; ++l) {
+      const std::string b = P + "encoder." + kBlocks[l];
+      const HostTensor* inw = find(ctx, b + ".self_attn.in_proj_weight");
+      const HostTensor* inb = find(ctx, b + ".self_attn.in_proj_bias");
+      const HostTensor* ow = find(ctx, b + ".self_attn.out_proj.weight");
+      const HostTensor* ob = find(ctx, b + ".self_attn.out_proj.bias");
+      const HostTensor* w1 = find(ctx, b + ".linear1.weight");
+      const HostTensor* b1 = find(ctx, b + ".linear1.bias");
+      const HostTensor* w2 = find(ctx, b + ".linear2.weight");
+      const HostTensor* b2 = find(ctx, b + ".linear2.bias");
+      const HostTensor* n1w = find(ctx, b + ".norm1.weight");
+      const HostTensor* n1b = find(ctx, b + ".norm1.bias");
+      const HostTensor* n2w = find(ctx, b + ".norm2.weight");
+      const HostTensor* n2b = find(ctx, b + ".norm2.bias");
+      const HostTensor *skw = nullptr, *skb = nullptr;
+      if (l >= 5) {
+        skw = find(ctx, P + "encoder.linear_blocks." + std::to_string(l - 5) + ".weight");
+        skb = find(ctx, P + "encoder.linear_blocks." + std::to_string(l - 5) + ".bias");
+      }
+      for (int rank = 0; rank < dn2::kCluster; ++rank) {
+        uint32_t* wb = blob2.data() + static_cast<size_t>(rank) * dn2::kRankVec4 * 4;
+        float* vb = vecs2.data() + static_cast<size_t>(rank) * dn2::kRankVecFloats;
+        const int t0 = (l < 5) ? 4 * l : 20 + 5 * (l - 5) + 1;   // index of this layer's QKV tile
+        int kind, off;
+        if (l >= 5) {   // skip-linear, K-split: input features [64 rank, +64) of cat(x, skip)
+          dn2::tile_info(t0 - 1, kind, off);
+          put_tile(wb + static_cast<size_t>(off) * 4, kind,
+                   [&](int f, int k) { return skw->data[static_cast<size_t>(f) * 256 + rank * 64 + k]; });
+          std::memcpy(vb + (t0 - 1) * 384, skb->data.data(), 128 * 4);
+        }
+        dn2::tile_info(t0, kind, off);       // q | k | v rows of head `rank` (96 features)
+        put_tile(wb + static_cast<size_t>(off) * 4, kind, [&](int f, int k) {
+          return inw->data[static_cast<size_t>((f / 32) * 128 + rank * 32 + (f % 32)) * 128 + k];
+        });
+        for (int f = 0; f < 96; ++f) vb[t0 * 384 + f] = inb->data[(f / 32) * 128 + rank * 32 + (f % 32)];
+        dn2::tile_info(t0 + 1, kind, off);   // out_proj, K-split by head
+        put_tile(wb + static_cast<size_t>(off) * 4, kind,
+                 [&](int f, int k) { return ow->data[static_cast<size_t>(f) * 128 + rank * 32 + k]; });
+        std::memcpy(vb + (t0 + 1) * 384, ob->data.data(), 128 * 4);
+        std::memcpy(vb + (t0 + 1) * 384 + 128, n1w->data.data(), 128 * 4);
+        std::memcpy(vb + (t0 + 1) * 384 + 256, n1b->data.data(), 128 * 4);
+        dn2::tile_info(t0 + 2, kind, off);   // linear1 rows [128 rank, +128)
+        put_tile(wb + static_cast<size_t>(off) * 4, kind,
+                 [&](int f, int k) { return w1->data[static_cast<size_t>(rank * 128 + f) * 128 + k]; });
+        std::memcpy(vb + (t0 + 2) * 384, b1->data.data() + rank * 128, 128 * 4);
+        dn2::tile_info(t0 + 3, kind, off);   // linear2, K-split over the rank's 128 hidden units
+        put_tile(wb + static_cast<size_t>(off) * 4, kind,
+                 [&](int f, int k) { return w2->data[static_cast<size_t>(f) * 512 + rank * 128 + k]; });
+        std::memcpy(vb + (t0 + 3) * 384, b2->data.data(), 128 * 4);
+        std::memcpy(vb + (t0 + 3) * 384 + 128, n2w->data.data(), 128 * 4);
+        std::memcpy(vb + (t0 + 3) * 384 + 256, n2b->data.data(), 128 * 4);
+      }
+    }
+  }
   // misc: time embedding (K-major), condition projections (K-major), PE, final norm, freqs
   NEED(tw1, P + "time_embedding.linear_1.weight", 128, 256);
   NEED(tb1, P + "time_embedding.linear_1.bias", 128);
@@ -427,6 +509,10 @@ int pack_denoiser(amuse_ctx* ctx, cudaStream_t st) {
   CU(d.blob.ensure(blob.size()));
   CU(d.misc.ensure(misc.size()));
   CU(cudaMemcpyAsync(d.blob.p, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice, st));
+  CU(d.blob2.ensure(blob2.size()));
+  CU(d.vecs2.ensure(vecs2.size()));
+  CU(cudaMemcpyAsync(d.blob2.p, blob2.data(), blob2.size() * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d.vecs2.p, vecs2.data(), vecs2.size() * 4, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(d.misc.p, misc.data(), misc.size() * 4, cudaMemcpyHostToDevice, st));
   CU(cudaStreamSynchronize(st));
   d.ready = true;
@@ -650,6 +736,34 @@ int run_denoise(amuse_ctx* ctx, int B, Schedule& sc, int clip, const float* late
   CU(launch_cond_tokens(ca, B, nc, st));   // a4 (+a5): once per call, step-invariant
   ctx->launches++;
 
+  if (!ctx->den_ffma) {
+    dn2::Params p{};
+    p.blob = reinterpret_cast<const uint4*>(d.blob2.p);
+    p.vecs = d.vecs2.p;
+    p.temb = sc.d_temb;
+    p.cond = ctx->cond.p;
+    p.pe01 = d.misc.p + d.pe;
+    p.final_norm = d.misc.p + d.fnorm;
+    p.latents0 = latents0;
+    p.step_noise = step_noise;
+    p.coef = sc.d_coef;
+    p.latents_out = latents_out;
+    p.prof = (ctx->prof_step >= 0) ? ctx->d_prof : nullptr;
+    p.prof_step = ctx->prof_step;
+    p.status = nullptr;
+    p.B = B;
+    p.T = 2 + nc;
+    p.n_steps = sc.n_steps;
+    p.dir_uses_eps = sc.dir_uses_eps ? 1 : 0;
+    p.clip = clip;
+    p.seed = seed;
+    p.seed_elem_base = elem_base;
+    p.prune_last = ctx->prune_last;
+    CU(dn2::launch(p, st));
+    ctx->launches++;
+    ctx->prof_step = -1;
+    return AMUSE_OK;
+  }
   dn::Params p{};
   p.blob = d.blob.p;
   p.temb = sc.d_temb;
@@ -1073,6 +1187,7 @@ int amuse_create(amuse_ctx** out, int device_ordinal) {
   default_alphas(c->alphas_cumprod);
   if (const char* e = getenv("AMUSE_DECODE_FFMA")) c->dec_use_tc = !(e[0] == '1');   // A/B switch for measurements
   if (const char* e = getenv("AMUSE_PRUNE_LAST")) c->prune_last = (e[0] != '0');
+  if (const char* e = getenv("AMUSE_DENOISE_FFMA")) c->den_ffma = (e[0] == '1');
   if (const char* e = getenv("AMUSE_WIDE_ROWS")) c->wide_rows = (e[0] != '0');
   if (cudaMalloc(&c->d_prof, 128 * sizeof(long long)) != cudaSuccess) {
     delete c;
@@ -1087,7 +1202,7 @@ void amuse_destroy(amuse_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   drop_schedules(ctx);
-  DevBuf* bufs[] = {&ctx->den.blob, &ctx->den.misc, &ctx->dec.arena, &ctx->cond, &ctx->lat_tmp, &ctx->lat_out,
+  DevBuf* bufs[] = {&ctx->den.blob, &ctx->den.misc, &ctx->den.blob2, &ctx->den.vecs2, &ctx->dec.arena, &ctx->cond, &ctx->lat_tmp, &ctx->lat_out,
                     &ctx->one_coef, &ctx->dXA, &ctx->dXB, &ctx->dXC, &ctx->dQKV, &ctx->dO, &ctx->dH, &ctx->dSkip,
                     &ctx->dFeats, &ctx->dCvec, &ctx->dZero, &ctx->h2d, &ctx->tX[0], &ctx->tX[1], &ctx->tX[2],
                     &ctx->tSkip, &ctx->tO, &ctx->tH, &ctx->mel_t, &ctx->enc.arena, &ctx->eFeat, &ctx->eEmb};
@@ -1188,7 +1303,7 @@ int amuse_schedule(amuse_ctx* ctx, int n_steps, int sampler, float eta, int32_t*
 
 int amuse_denoise(amuse_ctx* ctx, int B, int n_steps, int sampler, float eta, int clip_sample, const float* latents0,
                   const float* z_con, const float* z_emo, const float* z_sty, const float* step_noise,
-                  uint64_t seed, float* latents_out, void* stream) {
+                  uint64_t seed, uint64_t clip_offset, float* latents_out, void* stream) {
   if (int rc = check_ready(ctx, true, false)) return rc;
   if (B < 1 || !latents0 || !z_con || !latents_out) return fail(ctx, AMUSE_E_INVALID, "bad argument");
   cudaSetDevice(ctx->device);
@@ -1196,7 +1311,8 @@ int amuse_denoise(amuse_ctx* ctx, int B, int n_steps, int sampler, float eta, in
   Schedule* sc = nullptr;
   if (int rc = get_schedule(ctx, n_steps, sampler, eta, st, &sc)) return rc;
   const int clip = (clip_sample < 0) ? (sampler == AMUSE_SAMPLER_DDIM ? 1 : 0) : (clip_sample != 0);
-  return run_denoise(ctx, B, *sc, clip, latents0, z_con, z_emo, z_sty, step_noise, seed, 0, latents_out, st);
+  return run_denoise(ctx, B, *sc, clip, latents0, z_con, z_emo, z_sty, step_noise, seed, clip_offset * 128ull,
+                     latents_out, st);
 }
 
 int amuse_denoiser_eps(amuse_ctx* ctx, int B, int timestep, const float* sample, const float* z_con,
@@ -1265,8 +1381,8 @@ int amuse_rot6d_to_axis_angle(amuse_ctx* ctx, int64_t n, const float* d6, float*
 
 int amuse_diffusion_backward(amuse_ctx* ctx, int B, int n_steps, int sampler, float eta, int clip_sample,
                              const float* latents0, const float* z_con, const float* z_emo, const float* z_sty,
-                             const float* step_noise, uint64_t seed, float* latents_out, float* feats6d,
-                             float* poses, float* trans, void* stream) {
+                             const float* step_noise, uint64_t seed, uint64_t clip_offset, float* latents_out,
+                             float* feats6d, float* poses, float* trans, void* stream) {
   if (int rc = check_ready(ctx, true, true)) return rc;
   if (!poses) return fail(ctx, AMUSE_E_INVALID, "poses must not be NULL");
   cudaSetDevice(ctx->device);
@@ -1276,15 +1392,15 @@ int amuse_diffusion_backward(amuse_ctx* ctx, int B, int n_steps, int sampler, fl
     z = ctx->lat_out.p;
   }
   if (int rc = amuse_denoise(ctx, B, n_steps, sampler, eta, clip_sample, latents0, z_con, z_emo, z_sty, step_noise,
-                             seed, z, stream))
+                             seed, clip_offset, z, stream))
     return rc;
   return run_decode_any(ctx, B, z, feats6d, poses, trans, static_cast<cudaStream_t>(stream));
 }
 
 int amuse_diffusion_backward_host(amuse_ctx* ctx, int B, int n_steps, int sampler, float eta, int clip_sample,
                                   const float* latents0, const float* z_con, const float* z_emo,
-                                  const float* z_sty, const float* step_noise, uint64_t seed, float* poses,
-                                  float* trans, void* stream) {
+                                  const float* z_sty, const float* step_noise, uint64_t seed,
+                                  uint64_t clip_offset, float* poses, float* trans, void* stream) {
   if (int rc = check_ready(ctx, true, true)) return rc;
   if (B < 1 || !latents0 || !z_con || !poses) return fail(ctx, AMUSE_E_INVALID, "bad argument");
   cudaSetDevice(ctx->device);
@@ -1307,7 +1423,8 @@ int amuse_diffusion_backward_host(amuse_ctx* ctx, int B, int n_steps, int sample
   if (step_noise) CU(cudaMemcpyAsync(d_noise, step_noise, nn * 4, cudaMemcpyHostToDevice, st));
   if (int rc = amuse_diffusion_backward(ctx, B, n_steps, sampler, eta, clip_sample, d_l0, d_con,
                                         z_emo ? d_emo : nullptr, z_sty ? d_sty : nullptr,
-                                        step_noise ? d_noise : nullptr, seed, nullptr, nullptr, d_poses, d_trans,
+                                        step_noise ? d_noise : nullptr, seed, clip_offset, nullptr, nullptr, d_poses,
+                                        d_trans,
                                         stream))
     return rc;
   CU(cudaMemcpyAsync(poses, d_poses, np * 4, cudaMemcpyDeviceToHost, st));
@@ -1383,6 +1500,15 @@ int amuse_fbank(amuse_ctx* ctx, int B, int n_samples, const float* wave, float n
     CU(fb::upload_tables());
   }
   CU(fb::launch(wave, B, n_samples, ctx->mel_t.p, norm_mean, norm_std, fbank, st));
+  ctx->launches++;
+  return AMUSE_OK;
+}
+
+int amuse_debug_philox_normals(amuse_ctx* ctx, uint64_t seed, uint64_t clip_offset, int B, int n_steps, float* out,
+                               void* stream) {
+  if (!ctx || B < 1 || n_steps < 1 || n_steps > 65535 || !out) return fail(ctx, AMUSE_E_INVALID, "bad argument");
+  cudaSetDevice(ctx->device);
+  CU(launch_philox_export(seed, clip_offset, B, n_steps, out, static_cast<cudaStream_t>(stream)));
   ctx->launches++;
   return AMUSE_OK;
 }

@@ -322,13 +322,11 @@ __global__ void __launch_bounds__(kThreads, 1)
 }
 
 cudaError_t attention(const AttnArgs& a, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e =
-        cudaFuncSetAttribute(ast_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static PerDeviceOnce once;
+  if (cudaError_t e = once.run([] {
+        return cudaFuncSetAttribute(ast_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+      }))
+    return e;
   if (a.nb < 1) return cudaErrorInvalidValue;
   CUtensorMap tm[4];
   const int qk_rows = a.nb * kHeads * kTokP, v_rows = a.nb * kHeads * kHD;

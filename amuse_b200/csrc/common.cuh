@@ -7,7 +7,27 @@
 #error "amuse_b200 kernels are written for sm_100a (B200) only"
 #endif
 
+#include <mutex>
+
 namespace amuse {
+
+// Host: one-time initialisation that is PER DEVICE (cudaFuncSetAttribute, __constant__ uploads): a process may hold
+// contexts on several devices (amuse_create takes a device ordinal), possibly created from different threads.
+struct PerDeviceOnce {
+  std::mutex mu;
+  bool done[64] = {};
+  template <class F>
+  cudaError_t run(F&& init) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done[dev & 63]) return cudaSuccess;
+    if ((e = init()) != cudaSuccess) return e;
+    done[dev & 63] = true;
+    return cudaSuccess;
+  }
+};
 
 // ---- model constants (configs/diff_latent_v2.json:23-47, prior_emotional_fing.json:6-20)
 constexpr int kD = 128;        // latent / model width

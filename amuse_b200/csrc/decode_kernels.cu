@@ -297,16 +297,17 @@ __global__ void __launch_bounds__(128) self_attention_kernel(const float* __rest
   }
 }
 
+constexpr int kAttnMaxFrames = 320;
 template <bool PLANES>
 static cudaError_t launch_attn(const float* qkv, float* out, float* out_lo, int clips, int frames, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(frames) * 64 * sizeof(float);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(self_attention_kernel<PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  static PerDeviceOnce once;   // sized for the longest sequence either caller uses (302 encoder tokens)
+  if (smem > static_cast<size_t>(kAttnMaxFrames) * 64 * sizeof(float)) return cudaErrorInvalidValue;
+  if (cudaError_t e = once.run([] {
+        return cudaFuncSetAttribute(self_attention_kernel<PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kAttnMaxFrames * 64 * static_cast<int>(sizeof(float)));
+      }))
+    return e;
   dim3 grid((frames + 127) / 128, kHeads, clips);
   self_attention_kernel<PLANES><<<grid, 128, smem, st>>>(qkv, out, out_lo, frames);
   return cudaGetLastError();

@@ -30,9 +30,10 @@
 //     (SURVEY.md App. C), and at M <= 10 rows the tensor pipe would be operand-bandwidth bound.
 #include "denoise_loop.cuh"
 
-#include <curand_kernel.h>
+#include <mutex>
 
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace amuse {
 namespace dn {
@@ -444,13 +445,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   cluster_sync_all();   // every CTA of the cluster is resident, zero-filled and has its mbarriers
                         // initialised before any peer stores into its shared memory
 
-  // Philox stream per latent element (subsequence = global element index), so the noise a clip
-  // sees does not depend on how clips are packed into clusters or sharded over GPUs.
-  curandStatePhilox4_32_10_t rng;
+  // Stateless Philox draw per (global latent element, step) -- philox.cuh -- so the noise a clip sees does not
+  // depend on how clips are packed into clusters or sharded over GPUs.
   const bool use_rng = (p.step_noise == nullptr);
   const bool owns_elem = tid < S * 128;      // thread <-> latent element (S*128 <= 256)
-  if (use_rng && owns_elem)
-    curand_init(p.seed, p.seed_elem_base + static_cast<unsigned long long>(s_base) * 128ull + tid, 0, &rng);
+  const unsigned long long rng_elem = p.seed_elem_base + static_cast<unsigned long long>(s_base) * 128ull + tid;
 
   // software prefetch (one step ahead) of the tiny per-step global reads
   float temb_next = (tid < 128) ? __ldg(p.temb + tid) : 0.f;
@@ -861,7 +860,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       if (p.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
       float out = __fadd_rn(__fmul_rn(coef[2], x0), __fmul_rn(coef[3], p.dir_uses_eps ? e : x));
       if (coef[4] != 0.f) {
-        const float zn = use_rng ? curand_normal(&rng) : noise;
+        const float zn = use_rng ? philox_normal(p.seed, rng_elem, static_cast<uint32_t>(step)) : noise;
         out = __fadd_rn(out, __fmul_rn(coef[4], zn));
       }
       zs[tid] = out;
@@ -882,9 +881,11 @@ cudaError_t launch(const Params& p, cudaStream_t stream) {
   static const Kernel kernels[3][2] = {{denoise_loop_kernel<1, false, false>, denoise_loop_kernel<1, true, false>},
                                        {denoise_loop_kernel<2, false, false>, denoise_loop_kernel<2, true, false>},
                                        {denoise_loop_kernel<2, false, true>, denoise_loop_kernel<2, true, true>}};
+  static std::mutex mu;                  // two contexts on two threads may reach their first launch together
   static bool configured_dev[64] = {};   // attributes and __constant__ data are per device
   int dev = 0;
   cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
   bool& configured = configured_dev[dev & 63];
   if (!configured) {
     int2 tab[kTilesPerStep];

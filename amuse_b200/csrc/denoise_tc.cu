@@ -1,0 +1,739 @@
+// K1+K2 on the tensor cores: the whole N-step denoising loop of PretrainedLPDM_v1.diffusion_backward
+// (reference infer_ldm.py:142-161) as ONE persistent launch, every GEMM a tcgen05.mma.
+//
+// What one step computes (reference denoiser.py:135-204, cross_attention.py:41-64,259-272):
+//   x = [z | time token | con | emo | sty] + learned PE        (<= 5 tokens x 128 per clip)
+//   9 post-LN encoder layers with U-Net skips, final LayerNorm, eps = token 0
+//   scheduler update of z (DDIM eta / DDPM ancestral), clamp(x0) optional
+//
+// B200 mapping.  The loop is a chain of ~41 dependent small GEMMs per step with M = 5 rows per clip: it is bound
+// by the latency of that chain, and every evaluation needs all 8.8 MB of weights.
+//   * A cluster of 4 CTAs (one attention head each) owns 2 clips.  Each clip is an independent CHAIN run by its own
+//     4 warps; the two chains of a CTA share the tensor pipe and the weight tiles, and one chain's exchange /
+//     LayerNorm latency hides under the other's MMAs (measured, scripts/ubench_h16.cu: one chain alone 894 cycles
+//     per stage, two chains 1109 cycles for both).
+//   * GEMM orientation: D[128 output features x rows] = W[128 x K] . X[rows x K]^T with the WEIGHTS as the A operand
+//     in TMEM (M = 128 lanes) and the 5 activation rows as the shared-memory B operand (an MMA whose A operand is
+//     read from shared memory costs ~60 cycles whatever N is, a TMEM one ~19).  The accumulator comes back with
+//     tcgen05.ld as "thread f holds feature f of all rows", and the whole epilogue chain (bias, residual, exchange,
+//     LayerNorm, GELU, next B operand) stays in that layout: no transposition through shared memory.
+//   * fp32-class accuracy from fp16 operands ("3xFP16"): x = hi + lo'/2048 with hi = fp16(x), lo' = fp16((x-hi)*2048);
+//       W.x ~= W_hi.x_hi  +  2^-11 (W_hi.x_lo' + W_lo'.x_hi)
+//     The B operand carries x_hi in rows 0..15 and x_lo' in rows 16..31, so ONE N = 32 MMA with A = W_hi yields
+//     W_hi.x_hi (columns 0..15) and W_hi.x_lo' (columns 16..31), and one N = 16 MMA with A = W_lo' adds W_lo'.x_hi
+//     onto columns 16..31: 2 MMAs per 16 k (3xTF32 needs 6).  Measured error of a K = 128 stage against fp64:
+//     1.5e-6, the fp32 FMA chain 1.9e-6 (profiles/r02_ubench_h16.txt).  The hi/lo' planes are together exactly as
+//     many bytes as the fp32 weights.  Operands saturate at +-65504 (cvt.satfinite).
+//   * Weights: split 4 ways across the cluster exactly as the layers split (QKV and FFN1 by output feature = head /
+//     hidden slice, out_proj / FFN2 / skip-linear by input feature = K-split), pre-split into fp16 planes and
+//     laid out at amuse_finalize_weights in the order the producers read them.  8 producer warps stream the rank's
+//     1.86 MB per step from L2 with coalesced LDG.128 and write them into a 3-slot TMEM ring with tcgen05.st
+//     (measured 100 B/clk/SM, 20 TB/s chip-wide: profiles/r02_ubench_h16.txt); no shared-memory staging.
+//     full[slot] / empty[slot] mbarriers; empty is signalled by tcgen05.commit of both chains.
+//   * K-split stages end in an all-to-all exchange of partial sums through distributed shared memory with
+//     st.async (bytes are credited to the receiver's mbarrier; no cluster barrier inside the loop), receive
+//     buffers alternate per exchange (same protocol argument as the FFMA kernel, denoise_loop.cu).
+//   * LayerNorm in the feature-per-thread layout: per-warp shifted sums with a transposing butterfly (25 shuffles
+//     for 5 rows x 2 moments), combined across the 4 warps with Chan's parallel-variance formula.
+#include "denoise_tc.cuh"
+
+#include <cuda_fp16.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "philox.cuh"
+#include "tc_ptx.cuh"
+
+namespace amuse {
+namespace dn2 {
+
+namespace {
+
+using namespace tcp;
+
+constexpr int kRows = kTMax;
+constexpr uint32_t kSlotCols = 128, kSlots = 3;
+constexpr uint32_t kColD = kSlots * kSlotCols;   // chain c accumulates in columns [kColD + 32 c, +32)
+constexpr int kTmemCols = 512;
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {   // cute::UMMA::InstrDescriptor: D = F32, A = B = F16, K-major
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+constexpr uint32_t kIdescN32 = idesc_f16(128, 32), kIdescN16 = idesc_f16(128, 16);
+
+// ---- shared memory (bytes from the 1024-B aligned base)
+constexpr int kQkvLd = 100;                       // q|k|v row stride (floats)
+// receive slot of one peer: rows (0,1) as [128 features][2] | rows (2,3) as [128][2] | row 4 as [128]: every st.async of a
+// warp writes one contiguous 256-B / 128-B run of the peer's shared memory (a feature-major [128][5] slot -- 8-B stores
+// 24 B apart -- made every exchange 4x slower: 4.5k cycles per exchange stage, measured)
+constexpr int kPsSlot = 5 * 128 * 4;              // 2560
+constexpr int kPsBuf = 3 * kPsSlot;               // 7680: the 3 peers
+constexpr int oB = 0;                             // [2 boxes][32 rows][128 B] B operand (hi rows 0..15, lo' rows 16..31)
+constexpr int oPs = oB + 8192;                    // [2 buffers][3 peers][slot]
+constexpr int oQKV = oPs + 2 * kPsBuf + 1024;     // [5][100] floats
+constexpr int oSK = oQKV + 2048;                  // [4][5][128] floats: skip stack of the input blocks
+constexpr int oStat = oSK + 4 * kRows * 128 * 4;  // [4 warps][16] floats
+constexpr int kChainBytes = oStat + 1024;
+static_assert(kChainBytes % 1024 == 0, "the B operand of chain 1 must stay 1024-B aligned");
+constexpr int oBars = kChains * kChainBytes;
+constexpr int kSmemUsed = oBars + 256;
+constexpr int kSmemBytes = 120 * 1024;            // > half of the SM's shared memory: one CTA (= one 512-column TMEM allocation) per SM
+static_assert(kSmemUsed + 1024 <= kSmemBytes, "shared-memory carve-up");
+constexpr uint32_t kXchgBytes = 3u * 128u * 20u;  // what one exchange delivers to a chain: 3 peers x 128 features x 5 rows
+
+__constant__ int2 c_tiles[kTilesPerStep];   // (kind, offset in uint4) of tile i
+
+// ---- small PTX helpers
+__device__ __forceinline__ void bar_named(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void umma_f16_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
+      "r"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint4 (&r)[4]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0].x), "r"(r[0].y), "r"(r[0].z), "r"(r[0].w), "r"(r[1].x), "r"(r[1].y), "r"(r[1].z), "r"(r[1].w), "r"(r[2].x),
+      "r"(r[2].y), "r"(r[2].z), "r"(r[2].w), "r"(r[3].x), "r"(r[3].y), "r"(r[3].z), "r"(r[3].w)
+      : "memory");
+}
+// Columns [col, col+8) and [col+16, col+24) of my TMEM lane.  The registers are only defined after tcgen05.wait::ld,
+// so they are threaded through the wait as read-write operands: nothing that reads them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld_2x8(uint32_t taddr, float (&a)[8], float (&b)[8]) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr + 16)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a[i] = __uint_as_float(r[i]);
+    b[i] = __uint_as_float(r[8 + i]);
+  }
+}
+__device__ __forceinline__ void st_async_v2(uint32_t dst, float a, float b, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(dst),
+               "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_b32(uint32_t dst, float a, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst),
+               "r"(__float_as_uint(a)), "r"(mbar)
+               : "memory");
+}
+// fp16 hi / lo' planes of x (saturating: the operands of the MMAs must stay finite)
+__device__ __forceinline__ void split_h(float x, uint16_t& hi, uint16_t& lo) {
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(hi) : "f"(x));
+  const float r = (x - __half2float(__ushort_as_half(hi))) * 2048.0f;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(lo) : "f"(r));
+}
+
+struct Ctx {
+  const Params* p;
+  uint8_t* smem;
+  uint64_t* bars;
+  uint32_t tmem;
+  int* status;
+  __device__ __forceinline__ uint64_t* full(uint32_t s) const { return bars + s; }
+  __device__ __forceinline__ uint64_t* empty(uint32_t s) const { return bars + 3 + s; }
+  __device__ __forceinline__ uint64_t* dbar(int c) const { return bars + 6 + c; }
+  __device__ __forceinline__ uint64_t* xbar(int c, uint32_t i) const { return bars + 8 + c * 2 + i; }
+};
+// Bounded wait: a protocol bug must end the launch (trap -> the host sees a launch failure), never hang the GPU.
+__device__ __forceinline__ void wait_bar(const Ctx& k, uint64_t* bar, uint32_t parity) {
+  for (uint32_t i = 0; i < (1u << 26); ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  if (k.status) *k.status = 1;
+  __trap();
+}
+
+// ---------------------------------------------------------------- weight producers (8 warps)
+// Tile g (global sequence number over all steps) goes to TMEM slot g % 3.  Each warp owns one TMEM lane quadrant
+// (32 features) and every second 16-column unit of the tile: 4 x LDG.128 per unit and thread (512 contiguous bytes
+// per warp instruction), all units of a tile in flight at once, then tcgen05.st.x16 per unit.
+__device__ void producer_loop(const Ctx& k, int pw, int lane, uint32_t rank) {
+  const int q = pw & 3, grp = pw >> 2;
+  const uint32_t lane_base = k.tmem + (static_cast<uint32_t>(q * 32) << 16);
+  const uint4* src = k.p->blob + static_cast<size_t>(rank) * kRankVec4 + lane;
+  const uint32_t total = static_cast<uint32_t>(k.p->n_steps) * kTilesPerStep;
+  uint32_t t = 0, slot = 0, use = 0;   // tile in step, slot = g % 3, use = g / 3
+  for (uint32_t g = 0; g < total; ++g) {
+    const int2 ti = c_tiles[t];
+    const int kind = ti.x;
+    const int quads = (kind == kQKV) ? 3 : 4;
+    const int mine = ((kind == kWO) ? 2 : (kind == kSK) ? 4 : 8) >> 1;   // my units: grp, grp + 2, ...
+    const bool has = q < quads;
+    uint4 r[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (has && j < mine) {
+        const uint4* s = src + ti.y + ((grp + 2 * j) * quads + q) * 128;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r[j][i] = ldg_stream(s + i * 32);
+      }
+    if (use > 0) wait_bar(k, k.empty(slot), (use - 1) & 1);   // both chains' MMAs on the previous occupant are complete
+    tc_fence_after();
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (has && j < mine) tmem_st16(lane_base + slot * kSlotCols + (grp + 2 * j) * 16, r[j]);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(k.full(slot));
+    if (++t == kTilesPerStep) t = 0;
+    if (++slot == kSlots) {
+      slot = 0;
+      ++use;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- one clip's chain (4 warps, thread f <-> feature f)
+#define DN2_PROF(slot_)                                        \
+  do {                                                         \
+    if (do_prof) k.p->prof[(slot_)] = clock64();               \
+  } while (0)
+// stamps inside the stages of layer 1 (slots 100..127; scripts/quick_bench.py prints them)
+#define DN2_FINE(slot_)                                        \
+  do {                                                         \
+    if (do_prof && layer == 1) k.p->prof[(slot_)] = clock64(); \
+  } while (0)
+
+struct Chain {
+  const Ctx& k;
+  const int c, q, lane, f;
+  const uint32_t rank;
+  uint8_t* const base;        // this chain's shared memory
+  const uint32_t lane_taddr;  // TMEM address of my lane, column 0
+  const uint64_t bdesc;       // UMMA descriptor of the B operand
+  uint32_t g_slot = 0, g_use = 0, g_tile = 0;   // next weight tile: TMEM slot, use count of that slot, index in the step
+  uint32_t dphase = 0, xe = 0;
+  const int barid;
+  long long* fine = nullptr;   // debug: stamps inside gemm() of one stage (profile_arm)
+
+  __device__ Chain(const Ctx& k_, int c_, int q_, int lane_, uint32_t rank_)
+      : k(k_), c(c_), q(q_), lane(lane_), f(q_ * 32 + lane_), rank(rank_), base(k_.smem + c_ * kChainBytes),
+        lane_taddr(k_.tmem + (static_cast<uint32_t>(q_ * 32) << 16)), bdesc(umma_desc(smem_u32(k_.smem + c_ * kChainBytes + oB))),
+        barid(1 + c_) {}
+
+  __device__ __forceinline__ void bar() const { bar_named(barid); }
+  __device__ __forceinline__ const float* vec() const {   // bias | LN weight | LN bias of the tile about to be consumed
+    return k.p->vecs + static_cast<size_t>(rank) * kRankVecFloats + g_tile * 384 + f;
+  }
+
+  // B-operand element (row r, input feature kcol): hi at the returned offset, lo' 2048 bytes (16 rows) further
+  __device__ __forceinline__ void write_b(int kcol, const float (&v)[kRows]) const {
+    uint8_t* b0 = base + oB + (kcol >> 6) * 4096 + (kcol & 7) * 2;
+    const int cf = (kcol & 63) >> 3;
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      uint16_t h, l;
+      split_h(v[r], h, l);
+      uint8_t* d = b0 + r * 128 + ((cf ^ r) << 4);
+      *reinterpret_cast<uint16_t*>(d) = h;
+      *reinterpret_cast<uint16_t*>(d + 2048) = l;
+    }
+  }
+
+  // B operand complete -> MMAs of the next weight tile -> accumulator of my feature: y[r] = W.x (rows r < 5)
+  template <int K>
+  __device__ __forceinline__ void issue() const {
+    const uint32_t a = k.tmem + g_slot * kSlotCols, d = k.tmem + kColD + c * 32;
+    if (elect_one()) {
+#pragma unroll
+      for (int kk = 0; kk < K / 16; ++kk) {
+        const uint64_t bd = bdesc + (((kk >> 2) * 4096 + (kk & 3) * 32) >> 4);
+        umma_f16_ts(d, a + kk * 8, bd, kIdescN32, kk ? 1u : 0u);        // W_hi . [x_hi ; x_lo']
+        umma_f16_ts(d + 16, a + K / 2 + kk * 8, bd, kIdescN16, 1u);     // W_lo' . x_hi
+      }
+      umma_commit(k.dbar(c));
+      umma_commit(k.empty(g_slot));
+    }
+    __syncwarp();
+  }
+  __device__ __forceinline__ void gemm(int K, float (&y)[kRows]) {
+    fence_proxy_async();   // my B-operand stores -> async proxy
+    tc_fence_before();     // my tcgen05.ld of the previous accumulator -> before the MMAs that overwrite it
+    bar();
+    if (fine) fine[0] = clock64();
+    if (q == 0) {
+      wait_bar(k, k.full(g_slot), g_use & 1);
+      tc_fence_after();
+      if (fine) fine[1] = clock64();
+      if (K == 128) issue<128>();
+      else if (K == 64) issue<64>();
+      else issue<32>();
+      if (fine) fine[2] = clock64();
+    }
+    if (++g_tile == kTilesPerStep) g_tile = 0;
+    if (++g_slot == kSlots) {
+      g_slot = 0;
+      ++g_use;
+    }
+    wait_bar(k, k.dbar(c), dphase);
+    dphase ^= 1;
+    tc_fence_after();
+    if (fine) fine[3] = clock64();
+    float a[8], b[8];
+    tmem_ld_2x8(lane_taddr + kColD + c * 32, a, b);
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) y[r] = fmaf(b[r], 1.0f / 2048.0f, a[r]);
+  }
+
+  // ---- exchange of K-split partial sums (all-to-all over the 4 CTAs of the cluster)
+  __device__ __forceinline__ void xchg_arm() const {
+    if (f == 0) mbar_arrive_expect_tx(k.xbar(c, xe & 1), kXchgBytes);
+  }
+  __device__ __forceinline__ void xchg_send(const float (&y)[kRows]) const {
+    uint8_t* ps = base + oPs + (xe & 1) * kPsBuf + f * 8;
+    uint64_t* xb = k.xbar(c, xe & 1);
+#pragma unroll
+    for (uint32_t d = 1; d < kCluster; ++d) {
+      const uint32_t peer = (rank + d) & (kCluster - 1);
+      const uint32_t slot = (rank < peer) ? rank : rank - 1;   // my slot in the peer's receive buffer
+      const uint32_t dst = map_to_rank(ps + slot * kPsSlot, peer);
+      const uint32_t rb = map_to_rank(xb, peer);
+      st_async_v2(dst, y[0], y[1], rb);
+      st_async_v2(dst + 1024, y[2], y[3], rb);
+      st_async_b32(dst + 2048 - f * 4, y[4], rb);
+    }
+  }
+  __device__ __forceinline__ void xchg_recv(float (&v)[kRows]) {
+    wait_bar(k, k.xbar(c, xe & 1), (xe >> 1) & 1);
+    const uint8_t* ps = base + oPs + (xe & 1) * kPsBuf + f * 8;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const float2 a = *reinterpret_cast<const float2*>(ps + s * kPsSlot);
+      const float2 b = *reinterpret_cast<const float2*>(ps + s * kPsSlot + 1024);
+      const float e = *reinterpret_cast<const float*>(ps + s * kPsSlot + 2048 - f * 4);
+      v[0] += a.x;
+      v[1] += a.y;
+      v[2] += b.x;
+      v[3] += b.y;
+      v[4] += e;
+    }
+    ++xe;
+  }
+
+  // ---- LayerNorm over the 128 features of NR rows, feature f in this thread (nn.LayerNorm: biased variance, eps 1e-5)
+  // Per warp: shift by the warp's first feature, sum d and d^2 over the 32 lanes (transposing butterfly: the xor-16
+  // step hands the sums to the lower half-warp and the sums of squares to the upper one), then the 4 warps'
+  // (mean, M2) are merged with Chan's formula -- no cancellation whatever the row mean is.
+  template <int NR>
+  __device__ __forceinline__ void layernorm(float (&v)[kRows], float gam, float bet) const {
+    float t[NR], sh[NR];
+    const bool upper = (lane & 16) != 0;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      sh[r] = __shfl_sync(0xffffffffu, v[r], 0);
+      const float d = v[r] - sh[r];
+      const float s1 = d, s2 = d * d;
+      const float keep = upper ? s2 : s1, send = upper ? s1 : s2;
+      t[r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < NR; ++r) t[r] += __shfl_xor_sync(0xffffffffu, t[r], o);
+    float* st = reinterpret_cast<float*>(base + oStat) + q * 16;
+    if ((lane & 15) == 0) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) st[(upper ? 5 : 0) + r] = t[r];
+    }
+    if (lane == 1) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) st[10 + r] = sh[r];
+    }
+    bar();
+    // lane r < NR merges the 4 warps' moments of row r (Chan), then (mean, rstd) are broadcast to the warp
+    const float* sa = reinterpret_cast<const float*>(base + oStat) + ((lane < NR) ? lane : 0);
+    float mw[4], m2 = 0.f, mean = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float s1 = sa[w * 16], s2 = sa[w * 16 + 5];
+      mw[w] = fmaf(s1, 1.0f / 32.0f, sa[w * 16 + 10]);
+      m2 += fmaf(-s1 * (1.0f / 32.0f), s1, s2);
+      mean += mw[w];
+    }
+    mean *= 0.25f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float d = mw[w] - mean;
+      m2 = fmaf(32.0f * d, d, m2);
+    }
+    const float rstd = rsqrtf(fmaxf(m2 * (1.0f / 128.0f), 0.f) + kLnEps);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const float mr = __shfl_sync(0xffffffffu, mean, r), rr = __shfl_sync(0xffffffffu, rstd, r);
+      v[r] = (v[r] - mr) * rr * gam + bet;
+    }
+  }
+
+  // ---- attention of my head for the T tokens of the clip (cross_attention.py:264-266; nn.MultiheadAttention, 4 heads of 32)
+  // q (pre-scaled) | k | v rows are in shared memory; warps 0 and 1 of the chain: 3 query rows per warp, 10 lanes per row =
+  // 5 keys x 2 halves of the head dimension.  The output goes straight into the B operand of out_proj (K = 32).
+  __device__ __forceinline__ void attention(int T) const {
+    if (q >= 2) return;
+    const float* QKVs = reinterpret_cast<const float*>(base + oQKV);
+    const int at_slot = (lane < 30) ? lane / 10 : 0;
+    const int at_l = lane - (lane / 10) * 10;                   // position inside the slot: j * 2 + half
+    const bool at_live = (lane < 30) && (q * 3 + at_slot < T);
+    const int at_row = at_live ? q * 3 + at_slot : 0;
+    const int at_c = at_l & 1;
+    const bool at_key = at_live && (at_l >> 1) < T;
+    const int at_j = at_key ? (at_l >> 1) : 0;
+    const int at_src = at_slot * 10;
+    const bool at_pv = at_live && at_l < 8;
+    const float4* qv = reinterpret_cast<const float4*>(QKVs + at_row * kQkvLd + 16 * at_c);
+    const float4* kv = reinterpret_cast<const float4*>(QKVs + at_j * kQkvLd + 32 + 16 * at_c);
+    float p0, p1, p2, p3;
+    {
+      const float4 a = qv[0], b = kv[0];
+      p0 = a.x * b.x;
+      p1 = a.y * b.y;
+      p2 = a.z * b.z;
+      p3 = a.w * b.w;
+    }
+#pragma unroll
+    for (int i = 1; i < 4; ++i) {
+      const float4 a = qv[i], b = kv[i];
+      p0 = fmaf(a.x, b.x, p0);
+      p1 = fmaf(a.y, b.y, p1);
+      p2 = fmaf(a.z, b.z, p2);
+      p3 = fmaf(a.w, b.w, p3);
+    }
+    float sc = (p0 + p1) + (p2 + p3);
+    sc += __shfl_xor_sync(0xffffffffu, sc, 1);   // the two halves of the head dimension
+    float sj[5];
+#pragma unroll
+    for (int jj = 0; jj < 5; ++jj) sj[jj] = __shfl_sync(0xffffffffu, sc, at_src + 2 * jj);
+    float m = sj[0];
+#pragma unroll
+    for (int jj = 1; jj < 5; ++jj) m = (jj < T) ? fmaxf(m, sj[jj]) : m;
+    const float e = at_key ? expf(sc - m) : 0.f;
+    float ej[5];
+#pragma unroll
+    for (int jj = 0; jj < 5; ++jj) ej[jj] = __shfl_sync(0xffffffffu, e, at_src + 2 * jj);
+    const float sum = ((ej[0] + ej[1]) + (ej[2] + ej[3])) + ej[4];
+    if (at_pv) {   // 8 lanes per row: 4 head dimensions each
+      const float* vb = QKVs + 64 + 4 * at_l;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int jj = 0; jj < 5; ++jj)
+        if (jj < T) {
+          const float4 v4 = *reinterpret_cast<const float4*>(vb + jj * kQkvLd);
+          acc.x = fmaf(ej[jj], v4.x, acc.x);
+          acc.y = fmaf(ej[jj], v4.y, acc.y);
+          acc.z = fmaf(ej[jj], v4.z, acc.z);
+          acc.w = fmaf(ej[jj], v4.w, acc.w);
+        }
+      const float inv = __frcp_rn(sum);
+      const float o[4] = {acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv};
+      uint16_t h[4], l[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split_h(o[i], h[i], l[i]);
+      // element (row, k = 4 at_l .. +3): chunk (at_l >> 1) ^ row, 8 bytes at (at_l & 1) * 8
+      uint8_t* d = base + oB + at_row * 128 + ((((at_l >> 1) ^ at_row) & 7) << 4) + (at_l & 1) * 8;
+      *reinterpret_cast<uint2*>(d) = make_uint2(h[0] | (static_cast<uint32_t>(h[1]) << 16), h[2] | (static_cast<uint32_t>(h[3]) << 16));
+      *reinterpret_cast<uint2*>(d + 2048) = make_uint2(l[0] | (static_cast<uint32_t>(l[1]) << 16), l[2] | (static_cast<uint32_t>(l[3]) << 16));
+    }
+  }
+
+  __device__ void run();
+};
+
+__device__ void Chain::run() {
+  const Params& p = *k.p;
+  const int T = p.T;
+  const int cid = static_cast<int>(cluster_id_x());
+  const int clip = cid * kChains + c;
+  const bool do_prof_chain = (p.prof != nullptr) && cid == 0 && rank == 0 && c == 0 && f == 0;
+  float* const QKVs = reinterpret_cast<float*>(base + oQKV);
+  float* const SK = reinterpret_cast<float*>(base + oSK);
+
+  // per-thread constants: feature f of the PE rows, the condition tokens and the final norm
+  const float pe0 = p.pe01[f], pe1 = p.pe01[128 + f];
+  float ct[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) ct[j] = (j < T - 2) ? p.cond[(static_cast<size_t>(clip) * 3 + j) * 128 + f] : 0.f;
+  const float fn_g = p.final_norm[f], fn_b = p.final_norm[128 + f];
+  float z = p.latents0[static_cast<size_t>(clip) * 128 + f];
+  const bool use_rng = (p.step_noise == nullptr);
+  const unsigned long long elem = p.seed_elem_base + static_cast<unsigned long long>(clip) * 128ull + f;
+
+  // software prefetch (one step ahead) of the per-step global reads
+  float temb_next = __ldg(p.temb + f);
+  float coef_next[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) coef_next[i] = __ldg(p.coef + i);
+  float noise_next = use_rng ? 0.f : __ldg(p.step_noise + static_cast<size_t>(clip) * 128 + f);
+
+  float x[kRows];   // residual stream: feature f of the T token rows (replicated in the 4 CTAs)
+  const bool skip_writer = (f >> 6) == static_cast<int>(rank & 1);   // my feature is in this rank's K slice of cat(x, skip)
+
+  for (int step = 0; step < p.n_steps; ++step) {
+    const bool do_prof = do_prof_chain && step == p.prof_step;
+    DN2_PROF(0);
+    float coef[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) coef[i] = coef_next[i];
+    const float noise = noise_next;
+    const float temb = temb_next;
+    if (step + 1 < p.n_steps) {
+      temb_next = __ldg(p.temb + static_cast<size_t>(step + 1) * 128 + f);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) coef_next[i] = __ldg(p.coef + static_cast<size_t>(step + 1) * 5 + i);
+      if (!use_rng) noise_next = __ldg(p.step_noise + (static_cast<size_t>(step + 1) * p.B + clip) * 128 + f);
+    }
+    // ---- token rows (denoiser.py:174-181 + position_encoding.py:156)
+    x[0] = z + pe0;
+    x[1] = temb + pe1;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) x[2 + j] = ct[j];
+    write_b(f, x);
+    DN2_PROF(1);
+
+    for (int layer = 0; layer < kLayers; ++layer) {
+      float y[kRows];
+      // =============== output blocks: x = Linear(256->128)(cat(x, xs.pop())), K-split 64 per CTA (B written by the previous stage)
+      if (layer >= 5) {
+        const float bias = __ldg(vec());
+        xchg_arm();
+        gemm(64, y);
+        xchg_send(y);
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) y[r] += bias;
+        xchg_recv(y);
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) x[r] = y[r];
+        write_b(f, x);
+      }
+      DN2_PROF(2 + layer * 10 + 0);
+
+      // =============== QKV of my head (nn.MultiheadAttention in_proj; q scaled by head_dim^-0.5 after the bias)
+      {
+        const float bias = __ldg(vec());
+        gemm(128, y);
+        if (f < 96) {
+          const float sc = (q == 0) ? 0.17677669529663687f : 1.0f;
+#pragma unroll
+          for (int r = 0; r < kRows; ++r) QKVs[r * kQkvLd + f] = (y[r] + bias) * sc;
+        }
+        bar();
+      }
+      DN2_PROF(2 + layer * 10 + 1);
+      attention(T);
+      DN2_PROF(2 + layer * 10 + 2);
+
+      const bool pruned = p.prune_last && layer == kLayers - 1;   // only token 0 is read after the last layer
+      // =============== out_proj, K-split by head -> exchange -> + bias + residual -> LayerNorm 1
+      {
+        const float bias = __ldg(vec()), gam = __ldg(vec() + 128), bet = __ldg(vec() + 256);
+        xchg_arm();
+        DN2_FINE(100);
+        if (do_prof && layer == 1) fine = k.p->prof + 108;
+        gemm(32, y);
+        fine = nullptr;
+        DN2_FINE(101);
+        xchg_send(y);
+        DN2_FINE(102);
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) y[r] += bias + x[r];
+        xchg_recv(y);
+        DN2_PROF(2 + layer * 10 + 3);
+        if (pruned) layernorm<1>(y, gam, bet);
+        else layernorm<kRows>(y, gam, bet);
+        DN2_FINE(103);
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) x[r] = y[r];
+        write_b(f, x);
+      }
+      DN2_PROF(2 + layer * 10 + 4);
+
+      // =============== FFN1: my 128 hidden units, erf-GELU
+      {
+        const float bias = __ldg(vec());
+        if (do_prof && layer == 1) fine = k.p->prof + 112;
+        gemm(128, y);
+        fine = nullptr;
+        DN2_FINE(104);
+        if (pruned) {
+          y[0] = gelu_erf(y[0] + bias);
+        } else {
+#pragma unroll
+          for (int r = 0; r < kRows; ++r) y[r] = gelu_erf(y[r] + bias);
+        }
+        DN2_FINE(105);
+        write_b(f, y);
+      }
+      DN2_PROF(2 + layer * 10 + 5);
+
+      // =============== FFN2, K-split over my 128 hidden units -> exchange -> + bias + residual -> LayerNorm 2
+      {
+        const float bias = __ldg(vec()), gam = __ldg(vec() + 128), bet = __ldg(vec() + 256);
+        xchg_arm();
+        gemm(128, y);
+        xchg_send(y);
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) y[r] += bias + x[r];
+        xchg_recv(y);
+        DN2_PROF(2 + layer * 10 + 6);
+        if (pruned) layernorm<1>(y, gam, bet);
+        else layernorm<kRows>(y, gam, bet);
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) x[r] = y[r];
+        if (layer < 4) {
+#pragma unroll
+          for (int r = 0; r < kRows; ++r) SK[(layer * kRows + r) * 128 + f] = x[r];
+        }
+        if (layer + 1 < kLayers) {
+          if (layer + 1 >= 5) {   // next stage = skip-linear: my rank's 64-wide K slice of cat(x, skip of layer 8 - (layer + 1))
+            if (skip_writer) {
+              float sv[kRows];
+#pragma unroll
+              for (int r = 0; r < kRows; ++r) sv[r] = (rank < 2) ? x[r] : SK[((7 - layer) * kRows + r) * 128 + f];
+              write_b(f & 63, sv);
+            }
+          } else {
+            write_b(f, x);
+          }
+        }
+      }
+      DN2_PROF(2 + layer * 10 + 7);
+    }   // layers
+
+    // ---- encoder.norm on token 0 -> eps (cross_attention.py:62-63, denoiser.py:188), then the scheduler step (K2),
+    //      replicated in every CTA; op order of diffusers' step(): x0 = (x - sqrt(1-a) e) / sqrt(a); clamp;
+    //      x' = c2 x0 + c3 (e | x) + sigma z
+    {
+      float e5[kRows];
+      e5[0] = x[0];
+#pragma unroll
+      for (int r = 1; r < kRows; ++r) e5[r] = 0.f;
+      layernorm<1>(e5, fn_g, fn_b);
+      const float e = e5[0];
+      float x0 = __fdiv_rn(__fsub_rn(z, __fmul_rn(coef[1], e)), coef[0]);
+      if (p.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+      float out = __fadd_rn(__fmul_rn(coef[2], x0), __fmul_rn(coef[3], p.dir_uses_eps ? e : z));
+      if (coef[4] != 0.f) {
+        const float zn = use_rng ? philox_normal(p.seed, elem, static_cast<uint32_t>(step)) : noise;
+        out = __fadd_rn(out, __fmul_rn(coef[4], zn));
+      }
+      z = out;
+    }
+    DN2_PROF(2 + kLayers * 10);
+  }   // steps
+  if (rank == 0) p.latents_out[static_cast<size_t>(clip) * 128 + f] = z;
+}
+
+}  // namespace
+
+// ================================================================= the kernel
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
+    denoise_tc_kernel(const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cid = static_cast<int>(cluster_id_x());
+  const int S = min(kChains, p.B - cid * kChains);   // clips (active chains) of this cluster, >= 1 by grid construction
+
+  Ctx k;
+  k.p = &p;
+  k.smem = smem;
+  k.bars = reinterpret_cast<uint64_t*>(smem + oBars);
+  k.status = p.status;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + oBars + 128);
+
+  for (int i = tid; i < kSmemUsed / 4; i += kThreads) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+  __syncthreads();
+  if (tid == 0) {
+    for (uint32_t s = 0; s < kSlots; ++s) {
+      mbar_init(k.full(s), kProdWarps);
+      mbar_init(k.empty(s), static_cast<uint32_t>(S));
+    }
+    for (int c = 0; c < kChains; ++c) {
+      mbar_init(k.dbar(c), 1);
+      mbar_init(k.xbar(c, 0), 1);
+      mbar_init(k.xbar(c, 1), 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  k.tmem = *tmem_slot;
+  cluster_sync_all();   // every CTA of the cluster is resident, zero-filled and has its mbarriers initialised
+                        // before any peer stores into its shared memory
+
+  if (warp >= 4 * kChains) {
+    producer_loop(k, warp - 4 * kChains, lane, rank);
+  } else if ((warp >> 2) < S) {
+    Chain ch(k, warp >> 2, warp & 3, lane, rank);
+    ch.run();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(k.tmem);
+  }
+  cluster_sync_all();   // nobody leaves while a peer could still address its shared memory
+}
+
+size_t smem_bytes() { return static_cast<size_t>(kSmemBytes); }
+
+cudaError_t launch(const Params& p, cudaStream_t stream) {
+  static std::mutex mu;
+  static bool configured_dev[64] = {};   // attributes and __constant__ data are per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!configured_dev[dev & 63]) {
+      int2 tab[kTilesPerStep];
+      for (int i = 0; i < kTilesPerStep; ++i) tile_info(i, tab[i].x, tab[i].y);
+      cudaError_t e = cudaMemcpyToSymbol(c_tiles, tab, sizeof(tab));
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(denoise_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+      if (e != cudaSuccess) return e;
+      configured_dev[dev & 63] = true;
+    }
+  }
+  if (p.B < 1 || p.T < 2 || p.T > kTMax || p.n_steps < 1) return cudaErrorInvalidValue;
+  const int n_clusters = (p.B + kChains - 1) / kChains;
+  denoise_tc_kernel<<<dim3(n_clusters * kCluster), dim3(kThreads), kSmemBytes, stream>>>(p);
+  return cudaGetLastError();
+}
+
+void split_fp16(float x, uint16_t& hi, uint16_t& lo) {
+  auto sat = [](float v) { return v > 65504.f ? 65504.f : (v < -65504.f ? -65504.f : v); };
+  const __half h = __float2half_rn(sat(x));
+  const float r = (x - __half2float(h)) * 2048.0f;
+  const __half l = __float2half_rn(sat(r));
+  hi = __half_as_ushort(h);
+  lo = __half_as_ushort(l);
+}
+
+}  // namespace dn2
+}  // namespace amuse

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) fbank_kernel(const float* __restrict__ wa
 }
 
 double mel_scale(double f) { return 1127.0 * std::log(1.0 + f / 700.0); }
-bool g_tables = false;
+PerDeviceOnce g_tables;   // the __constant__ tables are per device
 }  // namespace
 
 // mel_t [257][128]: torchaudio.compliance.kaldi.get_mel_banks(128, 512, 16000, 20, 0, 100, -500, 1.0),
@@ -108,8 +108,7 @@ void mel_banks_host(float* mel_t) {
     }
 }
 
-cudaError_t upload_tables() {
-  if (g_tables) return cudaSuccess;
+cudaError_t upload_tables_once() {
   std::vector<float2> tw(256);
   std::vector<float> win(kWin);
   const double pi = 3.14159265358979323846;
@@ -119,10 +118,9 @@ cudaError_t upload_tables() {
   cudaError_t e = cudaMemcpyToSymbol(c_twiddle, tw.data(), sizeof(float2) * 256);
   if (e != cudaSuccess) return e;
   e = cudaMemcpyToSymbol(c_window, win.data(), sizeof(float) * kWin);
-  if (e != cudaSuccess) return e;
-  g_tables = true;
-  return cudaSuccess;
+  return e;
 }
+cudaError_t upload_tables() { return g_tables.run(upload_tables_once); }
 
 cudaError_t launch(const float* wave, int B, int n_samples, const float* mel_t, float norm_mean, float norm_std,
                    float* out, cudaStream_t st) {

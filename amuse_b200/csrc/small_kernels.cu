@@ -5,6 +5,7 @@
 #include "small_kernels.cuh"
 
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace amuse {
 
@@ -224,6 +225,20 @@ __global__ void __launch_bounds__(256) encoder_dist_kernel(const float* __restri
 }
 cudaError_t launch_encoder_dist(const float* hi, const float* lo, int nb, float* mu, float* logvar, cudaStream_t st) {
   encoder_dist_kernel<<<nb, 256, 0, st>>>(hi, lo, mu, logvar);
+  return cudaGetLastError();
+}
+
+// Debug export of the sampler's in-kernel noise: out[step][b][e] = philox_normal(seed, (clip_offset + b) * 128 + e, step),
+// the very function both denoise-loop kernels call (philox.cuh).
+__global__ void __launch_bounds__(128) philox_export_kernel(unsigned long long seed, unsigned long long clip_offset, int B,
+                                                            float* __restrict__ out) {
+  const int step = blockIdx.y, b = blockIdx.x, e = threadIdx.x;
+  out[(static_cast<size_t>(step) * B + b) * 128 + e] =
+      philox_normal(seed, (clip_offset + static_cast<unsigned long long>(b)) * 128ull + e, static_cast<uint32_t>(step));
+}
+cudaError_t launch_philox_export(unsigned long long seed, unsigned long long clip_offset, int B, int n_steps, float* out,
+                                 cudaStream_t st) {
+  philox_export_kernel<<<dim3(B, n_steps), 128, 0, st>>>(seed, clip_offset, B, out);
   return cudaGetLastError();
 }
 

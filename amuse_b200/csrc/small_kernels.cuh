@@ -31,6 +31,9 @@ cudaError_t launch_encoder_tokens(const float* emb, const float* gtok, const flo
                                   cudaStream_t st);
 // mu[b] = x[b*302 + 0], logvar[b] = x[b*302 + 1]  (hi + lo)
 cudaError_t launch_encoder_dist(const float* hi, const float* lo, int nb, float* mu, float* logvar, cudaStream_t st);
+// out [n_steps][B][128]: the N(0,1) draws the sampler kernels make for (seed, clip_offset) -- debug / test hook
+cudaError_t launch_philox_export(unsigned long long seed, unsigned long long clip_offset, int B, int n_steps, float* out,
+                                 cudaStream_t st);
 cudaError_t launch_add_planes(const float* hi, const float* lo, float* out, size_t n, cudaStream_t st);
 
 }  // namespace amuse

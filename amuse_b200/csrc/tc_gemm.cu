@@ -394,13 +394,11 @@ cudaError_t make_map(CUtensorMap* tm, const float* ptr, int rows, int cols, int 
 
 template <int EPI>
 cudaError_t launch(const CUtensorMap* tm, const GemmDesc& d, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e =
-        cudaFuncSetAttribute(tc_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static PerDeviceOnce once;
+  if (cudaError_t e = once.run([] {
+        return cudaFuncSetAttribute(tc_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+      }))
+    return e;
   dim3 grid((d.N + BN - 1) / BN, (d.M + BM - 1) / BM);
   tc_gemm_kernel<EPI><<<grid, kThreads, kSmemBytes, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], d);
   return cudaGetLastError();

@@ -255,18 +255,21 @@ namespace {
 
 template <int EPI>
 cudaError_t launch2(const CUtensorMap* tm, const GemmDesc& d, cudaStream_t st) {
-  static bool configured = false;
-  static int n_pairs_max = 0;
-  if (!configured) {
-    cudaError_t e =
-        cudaFuncSetAttribute(tc_gemm2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return e;
-    int dev = 0, sms = 0;
-    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-    n_pairs_max = sms / 2;
-    configured = true;
-  }
+  static PerDeviceOnce once;
+  static int pairs_of_dev[64] = {};
+  int dev = 0;
+  if (cudaError_t e = cudaGetDevice(&dev)) return e;
+  if (cudaError_t e = once.run([dev] {
+        cudaError_t e2 =
+            cudaFuncSetAttribute(tc_gemm2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e2 != cudaSuccess) return e2;
+        int sms = 0;
+        if ((e2 = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e2;
+        pairs_of_dev[dev & 63] = sms / 2;
+        return cudaSuccess;
+      }))
+    return e;
+  const int n_pairs_max = pairs_of_dev[dev & 63];
   const int tiles_m = (d.M + 2 * BM - 1) / (2 * BM), tiles_n = d.N / BN;
   const int n_pairs = tiles_m * tiles_n < n_pairs_max ? tiles_m * tiles_n : n_pairs_max;
   tc_gemm2_kernel<EPI><<<2 * n_pairs, kThreads, kSmemBytes, st>>>(tm[0], tm[1], tm[2], tm[3], d, tiles_m, tiles_n);

@@ -106,7 +106,9 @@ class Engine:
         return list(ts), torch.tensor(list(cf), dtype=torch.float32).view(n_steps, 5)
 
     def denoise(self, latents0, z_con, z_emo=None, z_sty=None, n_steps=50, sampler="ddim", eta=0.0,
-                clip_sample=None, step_noise=None, seed=0) -> torch.Tensor:
+                clip_sample=None, step_noise=None, seed=0, clip_offset=0) -> torch.Tensor:
+        """``clip_offset``: global index of the first clip of this call (Philox noise is keyed by global clip index,
+        so shards of a batch reproduce the un-sharded run; see include/amuse_b200.h)."""
         B = latents0.shape[0]
         if B == 0:   # an empty batch has nothing to launch; the reference returns empty tensors as well
             return self._empty(0, 128)
@@ -117,7 +119,7 @@ class Engine:
         clip = -1 if clip_sample is None else int(bool(clip_sample))
         with torch.cuda.device(self.device):
             self._check(self.lib.amuse_denoise(self._h, B, n_steps, _lib.SAMPLER[sampler], eta, clip, _ptr(l0),
-                                               _ptr(con), _ptr(emo), _ptr(sty), _ptr(noise), seed, _ptr(out),
+                                               _ptr(con), _ptr(emo), _ptr(sty), _ptr(noise), seed, clip_offset, _ptr(out),
                                                self._stream()))
         return out
 
@@ -177,7 +179,7 @@ class Engine:
         return out
 
     def diffusion_backward(self, latents0, z_con, z_emo=None, z_sty=None, n_steps=50, sampler="ddim", eta=0.0,
-                           clip_sample=None, step_noise=None, seed=0, want_latents=False, want_feats=False):
+                           clip_sample=None, step_noise=None, seed=0, want_latents=False, want_feats=False, clip_offset=0):
         """Device tensors in, device tensors out: {"poses": [B,300,55,3], "trans": [B,300,3]}."""
         B = latents0.shape[0]
         if B == 0:
@@ -198,7 +200,7 @@ class Engine:
         with torch.cuda.device(self.device):
             self._check(self.lib.amuse_diffusion_backward(
                 self._h, B, n_steps, _lib.SAMPLER[sampler], eta, clip, _ptr(l0), _ptr(con), _ptr(emo), _ptr(sty),
-                _ptr(noise), seed, _ptr(lat), _ptr(feats), _ptr(poses), _ptr(trans), self._stream()))
+                _ptr(noise), seed, clip_offset, _ptr(lat), _ptr(feats), _ptr(poses), _ptr(trans), self._stream()))
         out = {"poses": poses, "trans": trans}
         if want_latents:
             out["latents"] = lat
@@ -207,7 +209,7 @@ class Engine:
         return out
 
     def diffusion_backward_host(self, latents0, z_con, z_emo=None, z_sty=None, n_steps=50, sampler="ddim", eta=0.0,
-                                clip_sample=None, step_noise=None, seed=0, out_poses=None, out_trans=None):
+                                clip_sample=None, step_noise=None, seed=0, out_poses=None, out_trans=None, clip_offset=0):
         """HOST tensors in (ideally pinned), HOST tensors out; copies are inside the call."""
         B = latents0.shape[0]
         if B == 0:
@@ -223,7 +225,7 @@ class Engine:
         with torch.cuda.device(self.device):
             self._check(self.lib.amuse_diffusion_backward_host(
                 self._h, B, n_steps, _lib.SAMPLER[sampler], eta, clip, _ptr(l0), _ptr(con), _ptr(emo), _ptr(sty),
-                _ptr(noise), seed, _ptr(poses), _ptr(trans), self._stream()))
+                _ptr(noise), seed, clip_offset, _ptr(poses), _ptr(trans), self._stream()))
         return {"poses": poses, "trans": trans}
 
     def fbank(self, wave: torch.Tensor, norm_mean: float = -9.173025, norm_std: float = 5.062332) -> torch.Tensor:
@@ -260,6 +262,14 @@ class Engine:
             self._check(self.lib.amuse_debug_tc_gemm(self._h, epi, M, N, K, _ptr(A), _ptr(A2), K1, _ptr(W), _ptr(bias),
                                                      _ptr(R), _ptr(ln), _ptr(cvec), rows_per_clip, _ptr(out),
                                                      self._stream()))
+        return out
+
+    def philox_normals(self, seed: int, B: int, n_steps: int, clip_offset: int = 0) -> torch.Tensor:
+        """The N(0,1) draws the sampler makes in-kernel for ``step_noise=None``: [n_steps, B, 128] (debug / test hook)."""
+        out = torch.empty(n_steps, B, 128, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.amuse_debug_philox_normals(self._h, seed, clip_offset, B, n_steps, _ptr(out),
+                                                            self._stream()))
         return out
 
     # ------------------------------------------------------------------ introspection

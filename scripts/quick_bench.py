@@ -60,8 +60,15 @@ def main():
             row.append(st[base + j] - (prev if j == 0 else st[base + j - 1]))
         print(f"layer {l}: " + " ".join(f"{n}={c}" for n, c in zip(names, row)))
     print("final+update:", st[92] - st[2 + 8 * 10 + 7])
-    print("layer0 exchange waits: out_proj", st[5] - st[105], " ffn2", st[8] - st[108])
-    if st[112]:   # library built with -DAMUSE_FINE_PROF: inside the stages of layer 1 (thread 0)
+    if not st[100]:
+        print("layer0 exchange waits: out_proj", st[5] - st[105], " ffn2", st[8] - st[108])
+    if st[100] and st[108]:   # tensor-core kernel: stamps inside the out_proj and FFN1 stages of layer 1 (chain 0, thread 0)
+        print(f"fine oprj: pre={st[100] - st[14]} bar={st[108] - st[100]} full-wait={st[109] - st[108]} issue={st[110] - st[109]} "
+              f"mma-wait={st[111] - st[110]} ld={st[101] - st[111]} send={st[102] - st[101]} recv-wait={st[15] - st[102]} "
+              f"ln={st[103] - st[15]} write_b={st[16] - st[103]}")
+        print(f"fine ffn1: bar={st[112] - st[16]} full-wait={st[113] - st[112]} issue={st[114] - st[113]} mma-wait={st[115] - st[114]} "
+              f"ld={st[104] - st[115]} gelu={st[105] - st[104]} write_b={st[17] - st[105]}")
+    elif st[112]:   # library built with -DAMUSE_FINE_PROF: inside the stages of layer 1 (thread 0)
         print(f"fine qkv : acquire={st[120] - st[12]} gemm={st[121] - st[120]} park+sync={st[122] - st[121]} "
               f"gather={st[123] - st[122]} sync={st[13] - st[123]}")
         print(f"fine oprj: acquire={st[124] - st[14]} gemm={st[125] - st[124]} park+sync={st[126] - st[125]} "

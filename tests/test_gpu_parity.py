@@ -8,6 +8,8 @@ max(ABS_FLOOR, K * ref_err) of the fp64 result and within TOL32 of the reference
 """
 import numpy as np
 import pytest
+import os
+
 import torch
 
 from oracle import lpdm_ref as R
@@ -290,6 +292,19 @@ def test_full_size_ddpm1000_b64_properties(engine):
     b = engine.denoise(l0, con, emo, sty, n_steps=1000, sampler="ddpm", seed=11)
     c = engine.denoise(l0, con, emo, sty, n_steps=1000, sampler="ddpm", seed=12)
     assert torch.equal(a, b) and not torch.equal(a, c) and torch.isfinite(a).all()
+    # GPU-count invariance: the two halves of the batch, run as separate calls with their
+    # global clip offsets (what ranks 0 and 1 of a 2-GPU run do), draw the same Philox noise as the full run.
+    # Without the offset the second half would reuse the first half's noise stream and differ grossly.
+    lo = engine.denoise(l0[:32], con[:32], emo[:32], sty[:32], n_steps=1000, sampler="ddpm", seed=11, clip_offset=0)
+    hi = engine.denoise(l0[32:], con[32:], emo[32:], sty[32:], n_steps=1000, sampler="ddpm", seed=11, clip_offset=32)
+    halves = torch.cat([lo, hi])
+    if os.environ.get("AMUSE_DENOISE_FFMA", "0") == "1":
+        # the FFMA fallback kernel packs 1 or 2 clips per cluster with different K-split orders: same noise, fp32 reordering
+        assert (halves - a).abs().max().item() < 5e-3
+    else:
+        assert torch.equal(halves, a)     # one clip per chain whatever the batch: bit-identical
+    wrong = engine.denoise(l0[32:], con[32:], emo[32:], sty[32:], n_steps=1000, sampler="ddpm", seed=11, clip_offset=0)
+    assert (wrong - a[32:]).abs().max().item() > 1.0
     poses, trans = engine.decode(a)
     assert torch.isfinite(poses).all() and poses.shape == (B, 300, 55, 3)
     assert poses.abs().max().item() <= 3.1416 + 1e-3          # axis-angle magnitude is an angle in [0, pi]
