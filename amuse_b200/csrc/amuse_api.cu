@@ -383,8 +383,8 @@ int pack_denoiser(amuse_ctx* ctx, cudaStream_t st) {
   }
   // ---- the tensor-core loop kernel's streams (denoise_tc.cuh): per rank, tiles in consumption order, each tile the
   //      fp16 hi / lo' planes of a [128 features x K] A operand in the producers' read order; + bias / LayerNorm vectors
-  std::vector<uint32_t> blob2(static_cast<size_t>(dn2::kCluster) * dn2::kRankVec4 * 4, 0u);
-  std::vector<float> vecs2(static_cast<size_t>(dn2::kCluster) * dn2::kRankVecFloats, 0.f);
+  std::vector<uint32_t> blob2(static_cast<size_t>(dn2::kRanks) * dn2::kRankVec4 * 4, 0u);
+  std::vector<float> vecs2(static_cast<size_t>(dn2::kRanks) * dn2::kRankVecFloats, 0.f);
   {
     auto put_tile = [](uint32_t* dst, int kind, auto&& Wfk) {   // Wfk(f, k): weight of output feature f, input feature k
       const int K = dn2::tile_K(kind), quads = dn2::tile_quads(kind), units = dn2::tile_units(kind);
@@ -424,7 +424,7 @@ int pack_denoiser(amuse_ctx* ctx, cudaStream_t st) {
         skw = find(ctx, P + "encoder.linear_blocks." + std::to_string(l - 5) + ".weight");
         skb = find(ctx, P + "encoder.linear_blocks." + std::to_string(l - 5) + ".bias");
       }
-      for (int rank = 0; rank < dn2::kCluster; ++rank) {
+      for (int rank = 0; rank < dn2::kRanks; ++rank) {
         uint32_t* wb = blob2.data() + static_cast<size_t>(rank) * dn2::kRankVec4 * 4;
         float* vb = vecs2.data() + static_cast<size_t>(rank) * dn2::kRankVecFloats;
         const int t0 = (l < 5) ? 4 * l : 20 + 5 * (l - 5) + 1;   // index of this layer's QKV tile
@@ -759,6 +759,7 @@ int run_denoise(amuse_ctx* ctx, int B, Schedule& sc, int clip, const float* late
     p.seed = seed;
     p.seed_elem_base = elem_base;
     p.prune_last = ctx->prune_last;
+    if (const char* e = getenv("AMUSE_DN2_DEBUG")) p.debug_flags = atoi(e);
     CU(dn2::launch(p, st));
     ctx->launches++;
     ctx->prof_step = -1;
@@ -1189,11 +1190,11 @@ int amuse_create(amuse_ctx** out, int device_ordinal) {
   if (const char* e = getenv("AMUSE_PRUNE_LAST")) c->prune_last = (e[0] != '0');
   if (const char* e = getenv("AMUSE_DENOISE_FFMA")) c->den_ffma = (e[0] == '1');
   if (const char* e = getenv("AMUSE_WIDE_ROWS")) c->wide_rows = (e[0] != '0');
-  if (cudaMalloc(&c->d_prof, 128 * sizeof(long long)) != cudaSuccess) {
+  if (cudaMalloc(&c->d_prof, 256 * sizeof(long long)) != cudaSuccess) {
     delete c;
     return AMUSE_E_CUDA;
   }
-  cudaMemset(c->d_prof, 0, 128 * sizeof(long long));
+  cudaMemset(c->d_prof, 0, 256 * sizeof(long long));
   *out = c;
   return AMUSE_OK;
 }
@@ -1537,7 +1538,7 @@ int amuse_profile_arm(amuse_ctx* ctx, int step) {
   return AMUSE_OK;
 }
 int amuse_profile_read(amuse_ctx* ctx, int64_t* stamps, int n) {
-  if (!ctx || !stamps || n < 1 || n > 128) return fail(ctx, AMUSE_E_INVALID, "bad argument");
+  if (!ctx || !stamps || n < 1 || n > 256) return fail(ctx, AMUSE_E_INVALID, "bad argument");
   cudaSetDevice(ctx->device);
   CU(cudaMemcpy(stamps, ctx->d_prof, sizeof(long long) * n, cudaMemcpyDeviceToHost));
   return AMUSE_OK;

@@ -8,10 +8,12 @@
 //
 // B200 mapping.  The loop is a chain of ~41 dependent small GEMMs per step with M = 5 rows per clip: it is bound
 // by the latency of that chain, and every evaluation needs all 8.8 MB of weights.
-//   * A cluster of 4 CTAs (one attention head each) owns 2 clips.  Each clip is an independent CHAIN run by its own
-//     4 warps; the two chains of a CTA share the tensor pipe and the weight tiles, and one chain's exchange /
-//     LayerNorm latency hides under the other's MMAs (measured, scripts/ubench_h16.cu: one chain alone 894 cycles
-//     per stage, two chains 1109 cycles for both).
+//   * One clip per cluster of 2 CTAs (64 clips = 128 SMs, one wave up to 74 clips).  The layers split 4 ways as
+//     in the FFMA kernel (QKV / FFN1 by output feature = attention head / hidden slice, out_proj / FFN2 / skip-linear
+//     by input feature = K-split); CTA r owns the two "ranks" 2r and 2r+1, so a K-split stage exchanges its partial
+//     sums with ONE peer (2.5 KB through distributed shared memory) instead of three.  (Measured first: 4-CTA
+//     clusters with two one-clip chains sharing an SM -- 60.7 us/step: the 7.7 KB exchanges ran at the 21 B/clk
+//     DSMEM port rate and the two chains slowed each other by 26%.)
 //   * GEMM orientation: D[128 output features x rows] = W[128 x K] . X[rows x K]^T with the WEIGHTS as the A operand
 //     in TMEM (M = 128 lanes) and the 5 activation rows as the shared-memory B operand (an MMA whose A operand is
 //     read from shared memory costs ~60 cycles whatever N is, a TMEM one ~19).  The accumulator comes back with
@@ -24,17 +26,20 @@
 //     onto columns 16..31: 2 MMAs per 16 k (3xTF32 needs 6).  Measured error of a K = 128 stage against fp64:
 //     1.5e-6, the fp32 FMA chain 1.9e-6 (profiles/r02_ubench_h16.txt).  The hi/lo' planes are together exactly as
 //     many bytes as the fp32 weights.  Operands saturate at +-65504 (cvt.satfinite).
-//   * Weights: split 4 ways across the cluster exactly as the layers split (QKV and FFN1 by output feature = head /
-//     hidden slice, out_proj / FFN2 / skip-linear by input feature = K-split), pre-split into fp16 planes and
-//     laid out at amuse_finalize_weights in the order the producers read them.  8 producer warps stream the rank's
-//     1.86 MB per step from L2 with coalesced LDG.128 and write them into a 3-slot TMEM ring with tcgen05.st
-//     (measured 100 B/clk/SM, 20 TB/s chip-wide: profiles/r02_ubench_h16.txt); no shared-memory staging.
-//     full[slot] / empty[slot] mbarriers; empty is signalled by tcgen05.commit of both chains.
-//   * K-split stages end in an all-to-all exchange of partial sums through distributed shared memory with
-//     st.async (bytes are credited to the receiver's mbarrier; no cluster barrier inside the loop), receive
-//     buffers alternate per exchange (same protocol argument as the FFMA kernel, denoise_loop.cu).
-//   * LayerNorm in the feature-per-thread layout: per-warp shifted sums with a transposing butterfly (25 shuffles
-//     for 5 rows x 2 moments), combined across the 4 warps with Chan's parallel-variance formula.
+//   * Warp roles (17 warps):
+//       0-7   epilogue warps (q = TMEM lane quadrant, t = group).  N-split stages: group t drains the accumulator of
+//             rank 2r+t (its head / hidden slice, all 5 rows) as soon as THAT tile's MMAs commit; K-split stages: one
+//             accumulator, group 0 takes rows 0..2 and group 1 rows 3..4 (exchange, residual, LayerNorm per group).
+//       8-15  weight producers: the CTA's two rank streams (2 x 1.86 MB per step, pre-split fp16 planes laid out at
+//             amuse_finalize_weights in read order) from L2 with coalesced LDG.128 straight into a 3-slot TMEM ring
+//             with tcgen05.st -- no shared-memory staging (measured 100 B/clk/SM, 20 TB/s chip-wide,
+//             profiles/r02_ubench_h16.txt).  full[slot] / empty[slot] mbarriers, empty signalled by tcgen05.commit.
+//       16    MMA issuer: pre-waits the weight tiles, waits for "B operand ready" (one arrive per epilogue warp),
+//             issues both tiles of the stage and commits to the groups' accumulator barriers.
+//   * K-split stages end in an exchange of partial sums with the peer CTA: st.async into its shared memory, bytes
+//     credited to ITS mbarrier (no cluster barrier inside the loop); receive buffers alternate per exchange.
+//   * LayerNorm in the feature-per-thread layout: per-warp shifted sums with a transposing butterfly, the 4 warps of a
+//     group merged with Chan's parallel-variance formula by one lane per row.
 #include "denoise_tc.cuh"
 
 #include <cuda_fp16.h>
@@ -53,33 +58,36 @@ namespace {
 using namespace tcp;
 
 constexpr int kRows = kTMax;
+constexpr int kNR = 3;                            // rows per thread in the row-split (K-split) epilogues: group 0 rows 0..2, group 1 rows 3..4
 constexpr uint32_t kSlotCols = 128, kSlots = 3;
-constexpr uint32_t kColD = kSlots * kSlotCols;   // chain c accumulates in columns [kColD + 32 c, +32)
+constexpr uint32_t kColD = kSlots * kSlotCols;   // accumulator i in columns [kColD + 32 i, +32)
 constexpr int kTmemCols = 512;
 __host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {   // cute::UMMA::InstrDescriptor: D = F32, A = B = F16, K-major
   return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 constexpr uint32_t kIdescN32 = idesc_f16(128, 32), kIdescN16 = idesc_f16(128, 16);
 
-// ---- shared memory (bytes from the 1024-B aligned base)
+// ---- shared memory (bytes from the 1024-B aligned base).  B operands: K-major SWIZZLE_128B, 32 rows (x_hi rows 0..15,
+// x_lo' rows 16..31), one 4 KB box per 64 input features.  Three buffers, so that a group that finishes its tile of an
+// N-split stage early never writes the operand the other tile's MMAs are still reading.
 constexpr int kQkvLd = 100;                       // q|k|v row stride (floats)
-// receive slot of one peer: rows (0,1) as [128 features][2] | rows (2,3) as [128][2] | row 4 as [128]: every st.async of a
-// warp writes one contiguous 256-B / 128-B run of the peer's shared memory (a feature-major [128][5] slot -- 8-B stores
-// 24 B apart -- made every exchange 4x slower: 4.5k cycles per exchange stage, measured)
+constexpr int oBx = 0;                            // [2 boxes] K = 128: the token rows (input of QKV / FFN1 / skip-linear)
+constexpr int oBo = oBx + 8192;                   // [1 box]   K = 64: attention output of my two heads (input of out_proj)
+constexpr int oBh = oBo + 4096;                   // [4 boxes] K = 256: my two hidden slices after GELU (input of FFN2)
+// receive slot of the peer's partial sums: rows (0,1) as [128 features][2] | rows (3,4) as [128][2] | row 2 as [128]:
+// every st.async of a warp writes one contiguous 256-B / 128-B run of the peer's shared memory (a feature-major
+// [128][5] slot -- 8-B stores 24 B apart -- made every exchange 4x slower, measured)
 constexpr int kPsSlot = 5 * 128 * 4;              // 2560
-constexpr int kPsBuf = 3 * kPsSlot;               // 7680: the 3 peers
-constexpr int oB = 0;                             // [2 boxes][32 rows][128 B] B operand (hi rows 0..15, lo' rows 16..31)
-constexpr int oPs = oB + 8192;                    // [2 buffers][3 peers][slot]
-constexpr int oQKV = oPs + 2 * kPsBuf + 1024;     // [5][100] floats
-constexpr int oSK = oQKV + 2048;                  // [4][5][128] floats: skip stack of the input blocks
-constexpr int oStat = oSK + 4 * kRows * 128 * 4;  // [4 warps][16] floats
-constexpr int kChainBytes = oStat + 1024;
-static_assert(kChainBytes % 1024 == 0, "the B operand of chain 1 must stay 1024-B aligned");
-constexpr int oBars = kChains * kChainBytes;
+constexpr int oPs = oBh + 16384;                  // [2 buffers][slot]
+constexpr int oQKV = oPs + 2 * kPsSlot;           // [2 heads][5][100] floats
+constexpr int oSK = oQKV + 4096;                  // [4][5][128] floats: skip stack of the input blocks
+constexpr int oStat = oSK + 4 * kRows * 128 * 4;  // [2 groups][4 warps][16] floats
+constexpr int oBars = oStat + 512;
 constexpr int kSmemUsed = oBars + 256;
 constexpr int kSmemBytes = 120 * 1024;            // > half of the SM's shared memory: one CTA (= one 512-column TMEM allocation) per SM
+static_assert(oBo % 1024 == 0 && oBh % 1024 == 0, "B operands must be 1024-B aligned");
 static_assert(kSmemUsed + 1024 <= kSmemBytes, "shared-memory carve-up");
-constexpr uint32_t kXchgBytes = 3u * 128u * 20u;  // what one exchange delivers to a chain: 3 peers x 128 features x 5 rows
+constexpr uint32_t kXchgBytes = kPsSlot;          // what one exchange delivers: the peer's 128 features x 5 rows
 
 __constant__ int2 c_tiles[kTilesPerStep];   // (kind, offset in uint4) of tile i
 
@@ -154,42 +162,58 @@ struct Ctx {
   int* status;
   __device__ __forceinline__ uint64_t* full(uint32_t s) const { return bars + s; }
   __device__ __forceinline__ uint64_t* empty(uint32_t s) const { return bars + 3 + s; }
-  __device__ __forceinline__ uint64_t* dbar(int c) const { return bars + 6 + c; }
-  __device__ __forceinline__ uint64_t* xbar(int c, uint32_t i) const { return bars + 8 + c * 2 + i; }
+  __device__ __forceinline__ uint64_t* dbar(int i) const { return bars + 6 + i; }
+  __device__ __forceinline__ uint64_t* xbar(uint32_t i) const { return bars + 8 + i; }
+  __device__ __forceinline__ uint64_t* bready() const { return bars + 10; }
 };
-// Bounded wait: a protocol bug must end the launch (trap -> the host sees a launch failure), never hang the GPU.
+// mbarrier wait.  try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or ~10 us
+// pass) instead of re-issuing the probe -- 17 warps spin-polling mbarriers saturated the SM's shared-memory pipe and
+// made every shuffle / LDS of the epilogue warps 3-4x slower (LayerNorm 1500 cycles, measured).
+// Bounded: a protocol bug must end the launch (trap -> the host sees a launch failure), never hang the GPU.
+__device__ __forceinline__ bool try_wait_hint(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(10000u)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void wait_bar(const Ctx& k, uint64_t* bar, uint32_t parity) {
-  for (uint32_t i = 0; i < (1u << 26); ++i)
-    if (mbar_try_wait(bar, parity)) return;
+  for (uint32_t i = 0; i < (1u << 20); ++i)
+    if (try_wait_hint(bar, parity)) return;
   if (k.status) *k.status = 1;
   __trap();
 }
 
 // ---------------------------------------------------------------- weight producers (8 warps)
-// Tile g (global sequence number over all steps) goes to TMEM slot g % 3.  Each warp owns one TMEM lane quadrant
-// (32 features) and every second 16-column unit of the tile: 4 x LDG.128 per unit and thread (512 contiguous bytes
-// per warp instruction), all units of a tile in flight at once, then tcgen05.st.x16 per unit.
+// Tile g (global sequence number: stage-major, rank 2r then 2r+1) goes to TMEM slot g % 3.  Each warp owns one TMEM
+// lane quadrant (32 features) and every second 16-column unit of the tile: 4 x LDG.128 per unit and thread (512
+// contiguous bytes per warp instruction), all units of a tile in flight at once, then tcgen05.st.x16 per unit.
 __device__ void producer_loop(const Ctx& k, int pw, int lane, uint32_t rank) {
   const int q = pw & 3, grp = pw >> 2;
   const uint32_t lane_base = k.tmem + (static_cast<uint32_t>(q * 32) << 16);
-  const uint4* src = k.p->blob + static_cast<size_t>(rank) * kRankVec4 + lane;
-  const uint32_t total = static_cast<uint32_t>(k.p->n_steps) * kTilesPerStep;
-  uint32_t t = 0, slot = 0, use = 0;   // tile in step, slot = g % 3, use = g / 3
+  const uint4* src0 = k.p->blob + static_cast<size_t>(rank * kVirt) * kRankVec4 + lane;
+  const uint32_t total = static_cast<uint32_t>(k.p->n_steps) * kTilesPerStep * kVirt;
+  uint32_t stage = 0, slot = 0, use = 0;   // stage in step, slot = g % 3, use = g / 3
   for (uint32_t g = 0; g < total; ++g) {
-    const int2 ti = c_tiles[t];
+    const int2 ti = c_tiles[stage];
     const int kind = ti.x;
     const int quads = (kind == kQKV) ? 3 : 4;
     const int mine = ((kind == kWO) ? 2 : (kind == kSK) ? 4 : 8) >> 1;   // my units: grp, grp + 2, ...
-    const bool has = q < quads;
+    const bool has = (q < quads) && !(k.p->debug_flags & 1);
+    const uint4* src = src0 + (g & 1) * kRankVec4 + ti.y;
     uint4 r[4][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if (has && j < mine) {
-        const uint4* s = src + ti.y + ((grp + 2 * j) * quads + q) * 128;
+        const uint4* s = src + ((grp + 2 * j) * quads + q) * 128;
 #pragma unroll
         for (int i = 0; i < 4; ++i) r[j][i] = ldg_stream(s + i * 32);
       }
-    if (use > 0) wait_bar(k, k.empty(slot), (use - 1) & 1);   // both chains' MMAs on the previous occupant are complete
+    if (use > 0) wait_bar(k, k.empty(slot), (use - 1) & 1);   // the MMAs on the previous occupant are complete
     tc_fence_after();
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -198,7 +222,9 @@ __device__ void producer_loop(const Ctx& k, int pw, int lane, uint32_t rank) {
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(k.full(slot));
-    if (++t == kTilesPerStep) t = 0;
+    if (g & 1) {
+      if (++stage == kTilesPerStep) stage = 0;
+    }
     if (++slot == kSlots) {
       slot = 0;
       ++use;
@@ -206,7 +232,71 @@ __device__ void producer_loop(const Ctx& k, int pw, int lane, uint32_t rank) {
   }
 }
 
-// ---------------------------------------------------------------- one clip's chain (4 warps, thread f <-> feature f)
+// ---------------------------------------------------------------- MMA issuer (1 warp)
+template <int K>
+__device__ __forceinline__ void issue_tile(uint32_t a, uint32_t d, uint64_t bdesc, int jbase, bool acc0) {
+#pragma unroll
+  for (int kk = 0; kk < K / 16; ++kk) {
+    const int j = jbase + kk;   // 16-wide k-step of the B buffer: box j / 4, 32 bytes per step inside the 128-B row
+    const uint64_t bd = bdesc + static_cast<uint64_t>(((j >> 2) * 4096 + (j & 3) * 32) >> 4);
+    umma_f16_ts(d, a + kk * 8, bd, kIdescN32, (acc0 || kk) ? 1u : 0u);     // W_hi . [x_hi ; x_lo']
+    umma_f16_ts(d + 16, a + K / 2 + kk * 8, bd, kIdescN16, 1u);            // W_lo' . x_hi
+  }
+}
+__device__ void issuer_loop(const Ctx& k) {
+  const Params& p = *k.p;
+  const bool prof_cta = (p.prof != nullptr) && cluster_id_x() == 0 && cluster_ctarank() == 0;
+  const uint64_t dBx = umma_desc(smem_u32(k.smem + oBx)), dBo = umma_desc(smem_u32(k.smem + oBo)),
+                 dBh = umma_desc(smem_u32(k.smem + oBh));
+  uint32_t slot = 0, use = 0, bph = 0;
+  for (int step = 0; step < p.n_steps; ++step) {
+    for (int stage = 0; stage < kTilesPerStep; ++stage) {
+      const int kind = c_tiles[stage].x;
+      const bool nsplit = (kind == kQKV) || (kind == kW1);
+      const uint64_t bdesc = (kind == kWO) ? dBo : (kind == kW2) ? dBh : dBx;
+      const int ksteps = (kind == kWO) ? 2 : (kind == kSK) ? 4 : 8;
+      // the stage's two weight tiles (usually long in TMEM): observed here, while the epilogue warps are still busy
+      uint32_t s2 = slot + 1, u2 = use;
+      if (s2 == kSlots) {
+        s2 = 0;
+        ++u2;
+      }
+      wait_bar(k, k.full(slot), use & 1);
+      wait_bar(k, k.full(s2), u2 & 1);
+      wait_bar(k, k.bready(), bph);
+      bph ^= 1;
+      tc_fence_after();
+      const bool fine = prof_cta && step == p.prof_step && (stage == 5 || stage == 6);
+      if (fine && elect_one()) p.prof[stage == 5 ? 108 : 112] = clock64();
+      if (elect_one()) {
+#pragma unroll
+        for (int t = 0; t < kVirt; ++t) {
+          const uint32_t sl = t ? s2 : slot;
+          const uint32_t a = k.tmem + sl * kSlotCols;
+          const uint32_t d = k.tmem + kColD + (nsplit ? t * 32 : 0);
+          const int jbase = nsplit ? 0 : t * ksteps;
+          const bool acc0 = !nsplit && t > 0;
+          if (kind == kWO) issue_tile<32>(a, d, bdesc, jbase, acc0);
+          else if (kind == kSK) issue_tile<64>(a, d, bdesc, jbase, acc0);
+          else issue_tile<128>(a, d, bdesc, jbase, acc0);
+          if (nsplit) umma_commit(k.dbar(t));
+          else if (t == kVirt - 1) umma_commit(k.dbar(0));
+          umma_commit(k.empty(sl));
+        }
+      }
+      __syncwarp();
+      if (fine && elect_one()) p.prof[stage == 5 ? 109 : 113] = clock64();
+      slot = s2 + 1;
+      use = u2;
+      if (slot == kSlots) {
+        slot = 0;
+        ++use;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- the clip's epilogue warps (8 warps)
 #define DN2_PROF(slot_)                                        \
   do {                                                         \
     if (do_prof) k.p->prof[(slot_)] = clock64();               \
@@ -219,127 +309,115 @@ __device__ void producer_loop(const Ctx& k, int pw, int lane, uint32_t rank) {
 
 struct Chain {
   const Ctx& k;
-  const int c, q, lane, f;
+  const int q, t, lane, f;    // TMEM lane quadrant, group, lane, feature = TMEM lane
   const uint32_t rank;
-  uint8_t* const base;        // this chain's shared memory
+  uint8_t* const smem;
   const uint32_t lane_taddr;  // TMEM address of my lane, column 0
-  const uint64_t bdesc;       // UMMA descriptor of the B operand
-  uint32_t g_slot = 0, g_use = 0, g_tile = 0;   // next weight tile: TMEM slot, use count of that slot, index in the step
-  uint32_t dphase = 0, xe = 0;
-  const int barid;
-  long long* fine = nullptr;   // debug: stamps inside gemm() of one stage (profile_arm)
-
-  __device__ Chain(const Ctx& k_, int c_, int q_, int lane_, uint32_t rank_)
-      : k(k_), c(c_), q(q_), lane(lane_), f(q_ * 32 + lane_), rank(rank_), base(k_.smem + c_ * kChainBytes),
-        lane_taddr(k_.tmem + (static_cast<uint32_t>(q_ * 32) << 16)), bdesc(umma_desc(smem_u32(k_.smem + c_ * kChainBytes + oB))),
-        barid(1 + c_) {}
-
-  __device__ __forceinline__ void bar() const { bar_named(barid); }
-  __device__ __forceinline__ const float* vec() const {   // bias | LN weight | LN bias of the tile about to be consumed
-    return k.p->vecs + static_cast<size_t>(rank) * kRankVecFloats + g_tile * 384 + f;
+  uint32_t g_tile = 0;        // stage in the step
+  uint32_t dph0 = 0, dph1 = 0, xe = 0;
+  long long* wprof = nullptr; // debug: this warp's stamp row (lane 0 of every epilogue warp of cluster 0 / CTA 0), armed for
+                              // the out_proj and FFN1 stages of layer 1 of the profiled step
+  __device__ __forceinline__ void stamp(int point) const {
+    if (wprof) wprof[point] = clock64();
   }
 
-  // B-operand element (row r, input feature kcol): hi at the returned offset, lo' 2048 bytes (16 rows) further
-  __device__ __forceinline__ void write_b(int kcol, const float (&v)[kRows]) const {
-    uint8_t* b0 = base + oB + (kcol >> 6) * 4096 + (kcol & 7) * 2;
+  __device__ Chain(const Ctx& k_, int q_, int t_, int lane_, uint32_t rank_)
+      : k(k_), q(q_), t(t_), lane(lane_), f(q_ * 32 + lane_), rank(rank_), smem(k_.smem),
+        lane_taddr(k_.tmem + (static_cast<uint32_t>(q_ * 32) << 16)) {}
+
+  __device__ __forceinline__ void bar_group() const { bar_named(2 + t); }
+  // bias | LN weight | LN bias of the stage about to run, for weight rank 2 rank + v
+  __device__ __forceinline__ const float* vec(int v) const {
+    return k.p->vecs + static_cast<size_t>(rank * kVirt + v) * kRankVecFloats + g_tile * 384 + f;
+  }
+
+  // B-operand element (row, input feature kcol) of buffer `buf`: x_hi at the computed offset, x_lo' 16 rows (2048 B) further
+  template <int N>
+  __device__ __forceinline__ void write_b(int buf, int kcol, int row_first, const float (&v)[N], int n) const {
+    uint8_t* b0 = smem + buf + (kcol >> 6) * 4096 + (kcol & 7) * 2;
     const int cf = (kcol & 63) >> 3;
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      uint16_t h, l;
-      split_h(v[r], h, l);
-      uint8_t* d = b0 + r * 128 + ((cf ^ r) << 4);
-      *reinterpret_cast<uint16_t*>(d) = h;
-      *reinterpret_cast<uint16_t*>(d + 2048) = l;
-    }
+    for (int i = 0; i < N; ++i)
+      if (i < n) {
+        const int r = row_first + i;
+        uint16_t h, l;
+        split_h(v[i], h, l);
+        uint8_t* d = b0 + r * 128 + ((cf ^ r) << 4);
+        *reinterpret_cast<uint16_t*>(d) = h;
+        *reinterpret_cast<uint16_t*>(d + 2048) = l;
+      }
   }
 
-  // B operand complete -> MMAs of the next weight tile -> accumulator of my feature: y[r] = W.x (rows r < 5)
-  template <int K>
-  __device__ __forceinline__ void issue() const {
-    const uint32_t a = k.tmem + g_slot * kSlotCols, d = k.tmem + kColD + c * 32;
-    if (elect_one()) {
-#pragma unroll
-      for (int kk = 0; kk < K / 16; ++kk) {
-        const uint64_t bd = bdesc + (((kk >> 2) * 4096 + (kk & 3) * 32) >> 4);
-        umma_f16_ts(d, a + kk * 8, bd, kIdescN32, kk ? 1u : 0u);        // W_hi . [x_hi ; x_lo']
-        umma_f16_ts(d + 16, a + K / 2 + kk * 8, bd, kIdescN16, 1u);     // W_lo' . x_hi
-      }
-      umma_commit(k.dbar(c));
-      umma_commit(k.empty(g_slot));
-    }
-    __syncwarp();
-  }
-  __device__ __forceinline__ void gemm(int K, float (&y)[kRows]) {
+  // "my part of the B operand is written, and I am done with the accumulators": one arrive per warp
+  __device__ __forceinline__ void signal_b() const {
     fence_proxy_async();   // my B-operand stores -> async proxy
     tc_fence_before();     // my tcgen05.ld of the previous accumulator -> before the MMAs that overwrite it
-    bar();
-    if (fine) fine[0] = clock64();
-    if (q == 0) {
-      wait_bar(k, k.full(g_slot), g_use & 1);
-      tc_fence_after();
-      if (fine) fine[1] = clock64();
-      if (K == 128) issue<128>();
-      else if (K == 64) issue<64>();
-      else issue<32>();
-      if (fine) fine[2] = clock64();
-    }
-    if (++g_tile == kTilesPerStep) g_tile = 0;
-    if (++g_slot == kSlots) {
-      g_slot = 0;
-      ++g_use;
-    }
-    wait_bar(k, k.dbar(c), dphase);
-    dphase ^= 1;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(k.bready());
+  }
+  // N-split stage: the accumulator of my group's tile, all 5 rows
+  __device__ __forceinline__ void gemm_nsplit(float (&y)[kRows]) {
+    stamp(9);
+    signal_b();
+    wait_bar(k, k.dbar(t), t ? dph1 : dph0);
+    stamp(10);
+    dph0 ^= 1;
+    dph1 ^= 1;
+    ++g_tile;
     tc_fence_after();
-    if (fine) fine[3] = clock64();
     float a[8], b[8];
-    tmem_ld_2x8(lane_taddr + kColD + c * 32, a, b);
+    tmem_ld_2x8(lane_taddr + kColD + t * 32, a, b);
 #pragma unroll
     for (int r = 0; r < kRows; ++r) y[r] = fmaf(b[r], 1.0f / 2048.0f, a[r]);
   }
+  // K-split stage: one accumulator (the sum over my two ranks), my group's rows
+  __device__ __forceinline__ void gemm_ksplit(float (&y)[kNR]) {
+    stamp(0);
+    signal_b();
+    wait_bar(k, k.dbar(0), dph0);
+    stamp(1);
+    dph0 ^= 1;
+    ++g_tile;
+    tc_fence_after();
+    float a[8], b[8];
+    tmem_ld_2x8(lane_taddr + kColD, a, b);
+#pragma unroll
+    for (int i = 0; i < kNR; ++i) y[i] = t ? fmaf(b[3 + i], 1.0f / 2048.0f, a[3 + i]) : fmaf(b[i], 1.0f / 2048.0f, a[i]);
+  }
 
-  // ---- exchange of K-split partial sums (all-to-all over the 4 CTAs of the cluster)
+  // ---- exchange of the K-split partial sums with the peer CTA
   __device__ __forceinline__ void xchg_arm() const {
-    if (f == 0) mbar_arrive_expect_tx(k.xbar(c, xe & 1), kXchgBytes);
+    if (f == 0 && t == 0) mbar_arrive_expect_tx(k.xbar(xe & 1), kXchgBytes);
   }
-  __device__ __forceinline__ void xchg_send(const float (&y)[kRows]) const {
-    uint8_t* ps = base + oPs + (xe & 1) * kPsBuf + f * 8;
-    uint64_t* xb = k.xbar(c, xe & 1);
-#pragma unroll
-    for (uint32_t d = 1; d < kCluster; ++d) {
-      const uint32_t peer = (rank + d) & (kCluster - 1);
-      const uint32_t slot = (rank < peer) ? rank : rank - 1;   // my slot in the peer's receive buffer
-      const uint32_t dst = map_to_rank(ps + slot * kPsSlot, peer);
-      const uint32_t rb = map_to_rank(xb, peer);
-      st_async_v2(dst, y[0], y[1], rb);
-      st_async_v2(dst + 1024, y[2], y[3], rb);
-      st_async_b32(dst + 2048 - f * 4, y[4], rb);
+  __device__ __forceinline__ void xchg_send(const float (&y)[kNR]) const {
+    uint8_t* ps = smem + oPs + (xe & 1) * kPsSlot;
+    const uint32_t peer = rank ^ 1u;
+    const uint32_t rb = map_to_rank(k.xbar(xe & 1), peer);
+    if (t == 0) {
+      st_async_v2(map_to_rank(ps + f * 8, peer), y[0], y[1], rb);
+      st_async_b32(map_to_rank(ps + 2048 + f * 4, peer), y[2], rb);
+    } else {
+      st_async_v2(map_to_rank(ps + 1024 + f * 8, peer), y[0], y[1], rb);
     }
   }
-  __device__ __forceinline__ void xchg_recv(float (&v)[kRows]) {
-    wait_bar(k, k.xbar(c, xe & 1), (xe >> 1) & 1);
-    const uint8_t* ps = base + oPs + (xe & 1) * kPsBuf + f * 8;
-#pragma unroll
-    for (int s = 0; s < 3; ++s) {
-      const float2 a = *reinterpret_cast<const float2*>(ps + s * kPsSlot);
-      const float2 b = *reinterpret_cast<const float2*>(ps + s * kPsSlot + 1024);
-      const float e = *reinterpret_cast<const float*>(ps + s * kPsSlot + 2048 - f * 4);
-      v[0] += a.x;
-      v[1] += a.y;
-      v[2] += b.x;
-      v[3] += b.y;
-      v[4] += e;
-    }
+  __device__ __forceinline__ void xchg_recv(float (&v)[kNR]) {
+    wait_bar(k, k.xbar(xe & 1), (xe >> 1) & 1);
+    const uint8_t* ps = smem + oPs + (xe & 1) * kPsSlot;
+    const float2 a = *reinterpret_cast<const float2*>(ps + t * 1024 + f * 8);
+    v[0] += a.x;
+    v[1] += a.y;
+    if (t == 0) v[2] += *reinterpret_cast<const float*>(ps + 2048 + f * 4);
     ++xe;
   }
 
-  // ---- LayerNorm over the 128 features of NR rows, feature f in this thread (nn.LayerNorm: biased variance, eps 1e-5)
-  // Per warp: shift by the warp's first feature, sum d and d^2 over the 32 lanes (transposing butterfly: the xor-16
-  // step hands the sums to the lower half-warp and the sums of squares to the upper one), then the 4 warps'
-  // (mean, M2) are merged with Chan's formula -- no cancellation whatever the row mean is.
+  // ---- LayerNorm over the 128 features of my group's NR rows, feature f in this thread (nn.LayerNorm: biased
+  // variance, eps 1e-5).  Per warp: shift by the warp's first feature, sum d and d^2 over the 32 lanes (transposing
+  // butterfly: the xor-16 step hands the sums to the lower half-warp and the sums of squares to the upper one); lane r
+  // then merges the 4 warps' (mean, M2) of row r with Chan's formula -- no cancellation whatever the row mean is --
+  // and (mean, rstd) are broadcast to the warp.
   template <int NR>
-  __device__ __forceinline__ void layernorm(float (&v)[kRows], float gam, float bet) const {
-    float t[NR], sh[NR];
+  __device__ __forceinline__ void layernorm(float (&v)[kNR], float gam, float bet) const {
+    float tt[NR], sh[NR];
     const bool upper = (lane & 16) != 0;
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
@@ -347,29 +425,30 @@ struct Chain {
       const float d = v[r] - sh[r];
       const float s1 = d, s2 = d * d;
       const float keep = upper ? s2 : s1, send = upper ? s1 : s2;
-      t[r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      tt[r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
     }
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1)
 #pragma unroll
-      for (int r = 0; r < NR; ++r) t[r] += __shfl_xor_sync(0xffffffffu, t[r], o);
-    float* st = reinterpret_cast<float*>(base + oStat) + q * 16;
+      for (int r = 0; r < NR; ++r) tt[r] += __shfl_xor_sync(0xffffffffu, tt[r], o);
+    float* st = reinterpret_cast<float*>(smem + oStat) + (t * 4 + q) * 16;
     if ((lane & 15) == 0) {
 #pragma unroll
-      for (int r = 0; r < NR; ++r) st[(upper ? 5 : 0) + r] = t[r];
+      for (int r = 0; r < NR; ++r) st[(upper ? 4 : 0) + r] = tt[r];
     }
     if (lane == 1) {
 #pragma unroll
-      for (int r = 0; r < NR; ++r) st[10 + r] = sh[r];
+      for (int r = 0; r < NR; ++r) st[8 + r] = sh[r];
     }
-    bar();
-    // lane r < NR merges the 4 warps' moments of row r (Chan), then (mean, rstd) are broadcast to the warp
-    const float* sa = reinterpret_cast<const float*>(base + oStat) + ((lane < NR) ? lane : 0);
+    stamp(5);
+    bar_group();
+    stamp(6);
+    const float* sa = reinterpret_cast<const float*>(smem + oStat) + t * 64 + ((lane < NR) ? lane : 0);
     float mw[4], m2 = 0.f, mean = 0.f;
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
-      const float s1 = sa[w * 16], s2 = sa[w * 16 + 5];
-      mw[w] = fmaf(s1, 1.0f / 32.0f, sa[w * 16 + 10]);
+      const float s1 = sa[w * 16], s2 = sa[w * 16 + 4];
+      mw[w] = fmaf(s1, 1.0f / 32.0f, sa[w * 16 + 8]);
       m2 += fmaf(-s1 * (1.0f / 32.0f), s1, s2);
       mean += mw[w];
     }
@@ -387,12 +466,12 @@ struct Chain {
     }
   }
 
-  // ---- attention of my head for the T tokens of the clip (cross_attention.py:264-266; nn.MultiheadAttention, 4 heads of 32)
-  // q (pre-scaled) | k | v rows are in shared memory; warps 0 and 1 of the chain: 3 query rows per warp, 10 lanes per row =
-  // 5 keys x 2 halves of the head dimension.  The output goes straight into the B operand of out_proj (K = 32).
+  // ---- attention of head 2 rank + t for the T tokens of the clip (cross_attention.py:264-266; nn.MultiheadAttention, 4
+  // heads of 32).  q (pre-scaled) | k | v rows are in shared memory; warps q = 0, 1 of the group: 3 query rows per warp,
+  // 10 lanes per row = 5 keys x 2 halves of the head dimension.  The output goes straight into the B operand of out_proj.
   __device__ __forceinline__ void attention(int T) const {
     if (q >= 2) return;
-    const float* QKVs = reinterpret_cast<const float*>(base + oQKV);
+    const float* QKVs = reinterpret_cast<const float*>(smem + oQKV) + t * (kRows * kQkvLd);
     const int at_slot = (lane < 30) ? lane / 10 : 0;
     const int at_l = lane - (lane / 10) * 10;                   // position inside the slot: j * 2 + half
     const bool at_live = (lane < 30) && (q * 3 + at_slot < T);
@@ -450,8 +529,8 @@ struct Chain {
       uint16_t h[4], l[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) split_h(o[i], h[i], l[i]);
-      // element (row, k = 4 at_l .. +3): chunk (at_l >> 1) ^ row, 8 bytes at (at_l & 1) * 8
-      uint8_t* d = base + oB + at_row * 128 + ((((at_l >> 1) ^ at_row) & 7) << 4) + (at_l & 1) * 8;
+      // element (row, k = 32 t + 4 at_l .. +3): 16-B chunk (4 t + (at_l >> 1)) ^ row, 8 bytes at (at_l & 1) * 8
+      uint8_t* d = smem + oBo + at_row * 128 + ((((4 * t + (at_l >> 1)) ^ at_row) & 7) << 4) + (at_l & 1) * 8;
       *reinterpret_cast<uint2*>(d) = make_uint2(h[0] | (static_cast<uint32_t>(h[1]) << 16), h[2] | (static_cast<uint32_t>(h[3]) << 16));
       *reinterpret_cast<uint2*>(d + 2048) = make_uint2(l[0] | (static_cast<uint32_t>(l[1]) << 16), l[2] | (static_cast<uint32_t>(l[3]) << 16));
     }
@@ -463,11 +542,11 @@ struct Chain {
 __device__ void Chain::run() {
   const Params& p = *k.p;
   const int T = p.T;
-  const int cid = static_cast<int>(cluster_id_x());
-  const int clip = cid * kChains + c;
-  const bool do_prof_chain = (p.prof != nullptr) && cid == 0 && rank == 0 && c == 0 && f == 0;
-  float* const QKVs = reinterpret_cast<float*>(base + oQKV);
-  float* const SK = reinterpret_cast<float*>(base + oSK);
+  const int clip = static_cast<int>(cluster_id_x());
+  const bool do_prof_chain = (p.prof != nullptr) && clip == 0 && rank == 0 && t == 0 && f == 0;
+  float* const QKVs = reinterpret_cast<float*>(smem + oQKV) + t * (kRows * kQkvLd);
+  float* const SK = reinterpret_cast<float*>(smem + oSK);
+  const int row0 = t * kNR, nr = t ? 2 : 3;   // my rows in the row-split epilogues
 
   // per-thread constants: feature f of the PE rows, the condition tokens and the final norm
   const float pe0 = p.pe01[f], pe1 = p.pe01[128 + f];
@@ -475,7 +554,7 @@ __device__ void Chain::run() {
 #pragma unroll
   for (int j = 0; j < 3; ++j) ct[j] = (j < T - 2) ? p.cond[(static_cast<size_t>(clip) * 3 + j) * 128 + f] : 0.f;
   const float fn_g = p.final_norm[f], fn_b = p.final_norm[128 + f];
-  float z = p.latents0[static_cast<size_t>(clip) * 128 + f];
+  float z = p.latents0[static_cast<size_t>(clip) * 128 + f];   // group 0 owns the latent (replicated in the two CTAs)
   const bool use_rng = (p.step_noise == nullptr);
   const unsigned long long elem = p.seed_elem_base + static_cast<unsigned long long>(clip) * 128ull + f;
 
@@ -486,11 +565,13 @@ __device__ void Chain::run() {
   for (int i = 0; i < 5; ++i) coef_next[i] = __ldg(p.coef + i);
   float noise_next = use_rng ? 0.f : __ldg(p.step_noise + static_cast<size_t>(clip) * 128 + f);
 
-  float x[kRows];   // residual stream: feature f of the T token rows (replicated in the 4 CTAs)
-  const bool skip_writer = (f >> 6) == static_cast<int>(rank & 1);   // my feature is in this rank's K slice of cat(x, skip)
+  float x[kNR];   // residual stream: feature f of my group's token rows (replicated in the two CTAs)
 
   for (int step = 0; step < p.n_steps; ++step) {
     const bool do_prof = do_prof_chain && step == p.prof_step;
+    long long* const fine_warp = (p.prof != nullptr && clip == 0 && rank == 0 && lane == 0 && step == p.prof_step)
+                                     ? p.prof + 128 + (t * 4 + q) * 16
+                                     : nullptr;
     DN2_PROF(0);
     float coef[5];
 #pragma unroll
@@ -503,117 +584,115 @@ __device__ void Chain::run() {
       for (int i = 0; i < 5; ++i) coef_next[i] = __ldg(p.coef + static_cast<size_t>(step + 1) * 5 + i);
       if (!use_rng) noise_next = __ldg(p.step_noise + (static_cast<size_t>(step + 1) * p.B + clip) * 128 + f);
     }
-    // ---- token rows (denoiser.py:174-181 + position_encoding.py:156)
-    x[0] = z + pe0;
-    x[1] = temb + pe1;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) x[2 + j] = ct[j];
-    write_b(f, x);
+    g_tile = 0;
+    // ---- token rows (denoiser.py:174-181 + position_encoding.py:156): z, t, con | emo, sty
+    x[0] = t ? ct[1] : z + pe0;
+    x[1] = t ? ct[2] : temb + pe1;
+    x[2] = t ? 0.f : ct[0];
+    write_b(oBx, f, row0, x, nr);
     DN2_PROF(1);
 
     for (int layer = 0; layer < kLayers; ++layer) {
-      float y[kRows];
-      // =============== output blocks: x = Linear(256->128)(cat(x, xs.pop())), K-split 64 per CTA (B written by the previous stage)
+      // =============== output blocks: x = Linear(256->128)(cat(x, xs.pop())), K-split: CTA 0 holds x, CTA 1 the skip
       if (layer >= 5) {
-        const float bias = __ldg(vec());
+        float y[kNR];
+        const float bias = __ldg(vec(0));
         xchg_arm();
-        gemm(64, y);
+        gemm_ksplit(y);
         xchg_send(y);
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) y[r] += bias;
+        for (int i = 0; i < kNR; ++i) y[i] += bias;
         xchg_recv(y);
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) x[r] = y[r];
-        write_b(f, x);
+        for (int i = 0; i < kNR; ++i) x[i] = y[i];
+        write_b(oBx, f, row0, x, nr);
       }
       DN2_PROF(2 + layer * 10 + 0);
 
-      // =============== QKV of my head (nn.MultiheadAttention in_proj; q scaled by head_dim^-0.5 after the bias)
+      // =============== QKV of head 2 rank + t (nn.MultiheadAttention in_proj; q scaled by head_dim^-0.5 after the bias)
       {
-        const float bias = __ldg(vec());
-        gemm(128, y);
+        float y[kRows];
+        const float bias = __ldg(vec(t));
+        gemm_nsplit(y);
         if (f < 96) {
           const float sc = (q == 0) ? 0.17677669529663687f : 1.0f;
 #pragma unroll
           for (int r = 0; r < kRows; ++r) QKVs[r * kQkvLd + f] = (y[r] + bias) * sc;
         }
-        bar();
+        bar_group();
       }
       DN2_PROF(2 + layer * 10 + 1);
       attention(T);
       DN2_PROF(2 + layer * 10 + 2);
 
-      const bool pruned = p.prune_last && layer == kLayers - 1;   // only token 0 is read after the last layer
       // =============== out_proj, K-split by head -> exchange -> + bias + residual -> LayerNorm 1
       {
-        const float bias = __ldg(vec()), gam = __ldg(vec() + 128), bet = __ldg(vec() + 256);
+        float y[kNR];
+        const float bias = __ldg(vec(0)), gam = __ldg(vec(0) + 128), bet = __ldg(vec(0) + 256);
         xchg_arm();
-        DN2_FINE(100);
-        if (do_prof && layer == 1) fine = k.p->prof + 108;
-        gemm(32, y);
-        fine = nullptr;
-        DN2_FINE(101);
+        if (fine_warp && layer == 1) wprof = fine_warp;
+        gemm_ksplit(y);
+        stamp(2);
         xchg_send(y);
-        DN2_FINE(102);
+        stamp(3);
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) y[r] += bias + x[r];
+        for (int i = 0; i < kNR; ++i) y[i] += bias + x[i];
         xchg_recv(y);
+        stamp(4);
         DN2_PROF(2 + layer * 10 + 3);
-        if (pruned) layernorm<1>(y, gam, bet);
-        else layernorm<kRows>(y, gam, bet);
-        DN2_FINE(103);
+        layernorm<kNR>(y, gam, bet);
+        asm volatile("" ::"f"(y[0]), "f"(y[1]), "f"(y[2]));
+        stamp(7);
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) x[r] = y[r];
-        write_b(f, x);
+        for (int i = 0; i < kNR; ++i) x[i] = y[i];
+        write_b(oBx, f, row0, x, nr);
+        stamp(8);
       }
       DN2_PROF(2 + layer * 10 + 4);
 
-      // =============== FFN1: my 128 hidden units, erf-GELU
+      // =============== FFN1: hidden slice 2 rank + t, erf-GELU
       {
-        const float bias = __ldg(vec());
-        if (do_prof && layer == 1) fine = k.p->prof + 112;
-        gemm(128, y);
-        fine = nullptr;
-        DN2_FINE(104);
-        if (pruned) {
-          y[0] = gelu_erf(y[0] + bias);
-        } else {
+        float y[kRows];
+        const float bias = __ldg(vec(t));
+        gemm_nsplit(y);
+        stamp(11);
 #pragma unroll
-          for (int r = 0; r < kRows; ++r) y[r] = gelu_erf(y[r] + bias);
-        }
-        DN2_FINE(105);
-        write_b(f, y);
+        for (int r = 0; r < kRows; ++r) y[r] = gelu_erf(y[r] + bias);
+        asm volatile("" ::"f"(y[0]), "f"(y[1]), "f"(y[2]), "f"(y[3]), "f"(y[4]));
+        stamp(12);
+        write_b(oBh, t * 128 + f, 0, y, kRows);
+        stamp(13);
+        wprof = nullptr;
       }
       DN2_PROF(2 + layer * 10 + 5);
 
-      // =============== FFN2, K-split over my 128 hidden units -> exchange -> + bias + residual -> LayerNorm 2
+      // =============== FFN2, K-split over my 256 hidden units -> exchange -> + bias + residual -> LayerNorm 2
       {
-        const float bias = __ldg(vec()), gam = __ldg(vec() + 128), bet = __ldg(vec() + 256);
+        float y[kNR];
+        const float bias = __ldg(vec(0)), gam = __ldg(vec(0) + 128), bet = __ldg(vec(0) + 256);
         xchg_arm();
-        gemm(128, y);
+        gemm_ksplit(y);
         xchg_send(y);
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) y[r] += bias + x[r];
+        for (int i = 0; i < kNR; ++i) y[i] += bias + x[i];
         xchg_recv(y);
         DN2_PROF(2 + layer * 10 + 6);
-        if (pruned) layernorm<1>(y, gam, bet);
-        else layernorm<kRows>(y, gam, bet);
+        layernorm<kNR>(y, gam, bet);
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) x[r] = y[r];
+        for (int i = 0; i < kNR; ++i) x[i] = y[i];
         if (layer < 4) {
 #pragma unroll
-          for (int r = 0; r < kRows; ++r) SK[(layer * kRows + r) * 128 + f] = x[r];
+          for (int i = 0; i < kNR; ++i)
+            if (i < nr) SK[(layer * kRows + row0 + i) * 128 + f] = x[i];
         }
         if (layer + 1 < kLayers) {
-          if (layer + 1 >= 5) {   // next stage = skip-linear: my rank's 64-wide K slice of cat(x, skip of layer 8 - (layer + 1))
-            if (skip_writer) {
-              float sv[kRows];
+          if (layer + 1 >= 5 && rank == 1) {   // next stage = skip-linear: CTA 1's K slice of cat(x, skip) is the skip of layer 7 - layer
+            float sv[kNR];
 #pragma unroll
-              for (int r = 0; r < kRows; ++r) sv[r] = (rank < 2) ? x[r] : SK[((7 - layer) * kRows + r) * 128 + f];
-              write_b(f & 63, sv);
-            }
+            for (int i = 0; i < kNR; ++i) sv[i] = (i < nr) ? SK[((7 - layer) * kRows + row0 + i) * 128 + f] : 0.f;
+            write_b(oBx, f, row0, sv, nr);
           } else {
-            write_b(f, x);
+            write_b(oBx, f, row0, x, nr);
           }
         }
       }
@@ -621,15 +700,12 @@ __device__ void Chain::run() {
     }   // layers
 
     // ---- encoder.norm on token 0 -> eps (cross_attention.py:62-63, denoiser.py:188), then the scheduler step (K2),
-    //      replicated in every CTA; op order of diffusers' step(): x0 = (x - sqrt(1-a) e) / sqrt(a); clamp;
+    //      replicated in both CTAs; op order of diffusers' step(): x0 = (x - sqrt(1-a) e) / sqrt(a); clamp;
     //      x' = c2 x0 + c3 (e | x) + sigma z
-    {
-      float e5[kRows];
-      e5[0] = x[0];
-#pragma unroll
-      for (int r = 1; r < kRows; ++r) e5[r] = 0.f;
-      layernorm<1>(e5, fn_g, fn_b);
-      const float e = e5[0];
+    if (t == 0) {
+      float e3[kNR] = {x[0], 0.f, 0.f};
+      layernorm<1>(e3, fn_g, fn_b);
+      const float e = e3[0];
       float x0 = __fdiv_rn(__fsub_rn(z, __fmul_rn(coef[1], e)), coef[0]);
       if (p.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
       float out = __fadd_rn(__fmul_rn(coef[2], x0), __fmul_rn(coef[3], p.dir_uses_eps ? e : z));
@@ -641,7 +717,7 @@ __device__ void Chain::run() {
     }
     DN2_PROF(2 + kLayers * 10);
   }   // steps
-  if (rank == 0) p.latents_out[static_cast<size_t>(clip) * 128 + f] = z;
+  if (rank == 0 && t == 0) p.latents_out[static_cast<size_t>(clip) * 128 + f] = z;
 }
 
 }  // namespace
@@ -653,8 +729,6 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
-  const int cid = static_cast<int>(cluster_id_x());
-  const int S = min(kChains, p.B - cid * kChains);   // clips (active chains) of this cluster, >= 1 by grid construction
 
   Ctx k;
   k.p = &p;
@@ -668,13 +742,13 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   if (tid == 0) {
     for (uint32_t s = 0; s < kSlots; ++s) {
       mbar_init(k.full(s), kProdWarps);
-      mbar_init(k.empty(s), static_cast<uint32_t>(S));
+      mbar_init(k.empty(s), 1);
     }
-    for (int c = 0; c < kChains; ++c) {
-      mbar_init(k.dbar(c), 1);
-      mbar_init(k.xbar(c, 0), 1);
-      mbar_init(k.xbar(c, 1), 1);
-    }
+    mbar_init(k.dbar(0), 1);
+    mbar_init(k.dbar(1), 1);
+    mbar_init(k.xbar(0), 1);
+    mbar_init(k.xbar(1), 1);
+    mbar_init(k.bready(), kChainWarps);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc<kTmemCols>(tmem_slot);
@@ -682,14 +756,16 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   __syncthreads();
   tc_fence_after();
   k.tmem = *tmem_slot;
-  cluster_sync_all();   // every CTA of the cluster is resident, zero-filled and has its mbarriers initialised
-                        // before any peer stores into its shared memory
+  cluster_sync_all();   // both CTAs are resident, zero-filled and have their mbarriers initialised before either
+                        // stores into the other's shared memory
 
-  if (warp >= 4 * kChains) {
-    producer_loop(k, warp - 4 * kChains, lane, rank);
-  } else if ((warp >> 2) < S) {
-    Chain ch(k, warp >> 2, warp & 3, lane, rank);
+  if (warp < kChainWarps) {
+    Chain ch(k, warp & 3, warp >> 2, lane, rank);
     ch.run();
+  } else if (warp < kChainWarps + kProdWarps) {
+    producer_loop(k, warp - kChainWarps, lane, rank);
+  } else {
+    issuer_loop(k);
   }
 
   tc_fence_before();
@@ -698,7 +774,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     tc_fence_after();
     tmem_dealloc<kTmemCols>(k.tmem);
   }
-  cluster_sync_all();   // nobody leaves while a peer could still address its shared memory
+  cluster_sync_all();   // nobody leaves while the peer could still address its shared memory
 }
 
 size_t smem_bytes() { return static_cast<size_t>(kSmemBytes); }
@@ -721,8 +797,7 @@ cudaError_t launch(const Params& p, cudaStream_t stream) {
     }
   }
   if (p.B < 1 || p.T < 2 || p.T > kTMax || p.n_steps < 1) return cudaErrorInvalidValue;
-  const int n_clusters = (p.B + kChains - 1) / kChains;
-  denoise_tc_kernel<<<dim3(n_clusters * kCluster), dim3(kThreads), kSmemBytes, stream>>>(p);
+  denoise_tc_kernel<<<dim3(p.B * kCluster), dim3(kThreads), kSmemBytes, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -8,10 +8,12 @@
 namespace amuse {
 namespace dn2 {
 
-constexpr int kCluster = 4;            // CTAs per cluster = attention heads (one head per CTA)
-constexpr int kChains = 2;             // clips per cluster; each clip is an independent "chain" of 4 warps
+constexpr int kCluster = 2;            // CTAs per cluster; one clip per cluster
+constexpr int kVirt = 2;               // weight "ranks" per CTA: CTA r owns attention heads / hidden slices 2r and 2r + 1
+constexpr int kRanks = kCluster * kVirt;   // the layers split 4 ways (one attention head per rank)
+constexpr int kChainWarps = 8;         // epilogue warps: (TMEM lane quadrant q, tile / row group t)
 constexpr int kProdWarps = 8;          // weight producers: global (L2) -> registers -> tcgen05.st
-constexpr int kThreads = (4 * kChains + kProdWarps) * 32;
+constexpr int kThreads = (kChainWarps + kProdWarps + 1) * 32;   // + the MMA issuer warp
 constexpr int kTMax = 5;               // tokens per clip: z, t, con, emo, sty (denoiser.py:174,180)
 constexpr int kTilesPerStep = 40;      // 9 layers x 4 weight tiles + 4 skip-linear tiles
 
@@ -53,8 +55,8 @@ __host__ __device__ inline void tile_info(int i, int& kind, int& off_vec4) {
 }
 
 struct Params {
-  const uint4* blob;         // [kCluster][kRankVec4]
-  const float* vecs;         // [kCluster][kRankVecFloats]
+  const uint4* blob;         // [kRanks][kRankVec4]
+  const float* vecs;         // [kRanks][kRankVecFloats]
   const float* temb;         // [n_steps][128]   time tokens (a3), batch-invariant
   const float* cond;         // [B][3][128]      condition tokens + their PE rows (a4+a5); first T-2 valid
   const float* pe01;         // [2][128]         query_pos.pe rows 0 and 1
@@ -63,7 +65,7 @@ struct Params {
   const float* step_noise;   // nullable [n_steps][B][128]
   const float* coef;         // [n_steps][5]     sqrt(a), sqrt(1-a), c_x0, c_dir, sigma
   float* latents_out;        // [B][128]
-  long long* prof;           // nullable: clock64 stamps of cluster 0 / rank 0 / chain 0 (debug)
+  long long* prof;           // nullable: clock64 stamps of cluster 0 / CTA 0 / thread 0 (debug)
   int* status;               // nullable: set to 1 if a bounded wait expired (the kernel then traps)
   int B, T, n_steps;
   int dir_uses_eps;          // 1: x' = c2 x0 + c3 eps (DDIM);  0: x' = c2 x0 + c3 x (DDPM posterior mean)
@@ -72,6 +74,7 @@ struct Params {
   unsigned long long seed_elem_base;   // global index of this launch's first latent element (multi-GPU shards)
   int prof_step;
   int prune_last;            // last layer evaluated for token 0 only (same result)
+  int debug_flags;           // timing experiments only (results are garbage): 1 = producers skip the loads and stores
 };
 
 size_t smem_bytes();
