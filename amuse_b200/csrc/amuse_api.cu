@@ -425,33 +425,37 @@ int pack_denoiser(amuse_ctx* ctx, cudaStream_t st) {
         skb = find(ctx, P + "encoder.linear_blocks." + std::to_string(l - 5) + ".bias");
       }
       for (int rank = 0; rank < dn2::kRanks; ++rank) {
-        uint32_t* wb = blob2.data() + static_cast<size_t>(rank) * dn2::kRankVec4 * 4;
+        // CTA rank / 2 streams its two weight ranks interleaved per stage: [stage][rank % 2] tiles, consumption order
+        uint32_t* const cta = blob2.data() + static_cast<size_t>(rank / 2) * 2 * dn2::kRankVec4 * 4;
+        auto wb_tile = [&](int kind_, int off_) {
+          return cta + (static_cast<size_t>(2) * off_ + static_cast<size_t>(rank % 2) * dn2::tile_vec4(kind_)) * 4;
+        };
         float* vb = vecs2.data() + static_cast<size_t>(rank) * dn2::kRankVecFloats;
         const int t0 = (l < 5) ? 4 * l : 20 + 5 * (l - 5) + 1;   // index of this layer's QKV tile
         int kind, off;
         if (l >= 5) {   // skip-linear, K-split: input features [64 rank, +64) of cat(x, skip)
           dn2::tile_info(t0 - 1, kind, off);
-          put_tile(wb + static_cast<size_t>(off) * 4, kind,
+          put_tile(wb_tile(kind, off), kind,
                    [&](int f, int k) { return skw->data[static_cast<size_t>(f) * 256 + rank * 64 + k]; });
           std::memcpy(vb + (t0 - 1) * 384, skb->data.data(), 128 * 4);
         }
         dn2::tile_info(t0, kind, off);       // q | k | v rows of head `rank` (96 features)
-        put_tile(wb + static_cast<size_t>(off) * 4, kind, [&](int f, int k) {
+        put_tile(wb_tile(kind, off), kind, [&](int f, int k) {
           return inw->data[static_cast<size_t>((f / 32) * 128 + rank * 32 + (f % 32)) * 128 + k];
         });
         for (int f = 0; f < 96; ++f) vb[t0 * 384 + f] = inb->data[(f / 32) * 128 + rank * 32 + (f % 32)];
         dn2::tile_info(t0 + 1, kind, off);   // out_proj, K-split by head
-        put_tile(wb + static_cast<size_t>(off) * 4, kind,
+        put_tile(wb_tile(kind, off), kind,
                  [&](int f, int k) { return ow->data[static_cast<size_t>(f) * 128 + rank * 32 + k]; });
         std::memcpy(vb + (t0 + 1) * 384, ob->data.data(), 128 * 4);
         std::memcpy(vb + (t0 + 1) * 384 + 128, n1w->data.data(), 128 * 4);
         std::memcpy(vb + (t0 + 1) * 384 + 256, n1b->data.data(), 128 * 4);
         dn2::tile_info(t0 + 2, kind, off);   // linear1 rows [128 rank, +128)
-        put_tile(wb + static_cast<size_t>(off) * 4, kind,
+        put_tile(wb_tile(kind, off), kind,
                  [&](int f, int k) { return w1->data[static_cast<size_t>(rank * 128 + f) * 128 + k]; });
         std::memcpy(vb + (t0 + 2) * 384, b1->data.data() + rank * 128, 128 * 4);
         dn2::tile_info(t0 + 3, kind, off);   // linear2, K-split over the rank's 128 hidden units
-        put_tile(wb + static_cast<size_t>(off) * 4, kind,
+        put_tile(wb_tile(kind, off), kind,
                  [&](int f, int k) { return w2->data[static_cast<size_t>(f) * 512 + rank * 128 + k]; });
         std::memcpy(vb + (t0 + 3) * 384, b2->data.data(), 128 * 4);
         std::memcpy(vb + (t0 + 3) * 384 + 128, n2w->data.data(), 128 * 4);
@@ -1190,11 +1194,11 @@ int amuse_create(amuse_ctx** out, int device_ordinal) {
   if (const char* e = getenv("AMUSE_PRUNE_LAST")) c->prune_last = (e[0] != '0');
   if (const char* e = getenv("AMUSE_DENOISE_FFMA")) c->den_ffma = (e[0] == '1');
   if (const char* e = getenv("AMUSE_WIDE_ROWS")) c->wide_rows = (e[0] != '0');
-  if (cudaMalloc(&c->d_prof, 256 * sizeof(long long)) != cudaSuccess) {
+  if (cudaMalloc(&c->d_prof, 512 * sizeof(long long)) != cudaSuccess) {
     delete c;
     return AMUSE_E_CUDA;
   }
-  cudaMemset(c->d_prof, 0, 256 * sizeof(long long));
+  cudaMemset(c->d_prof, 0, 512 * sizeof(long long));
   *out = c;
   return AMUSE_OK;
 }
@@ -1538,7 +1542,7 @@ int amuse_profile_arm(amuse_ctx* ctx, int step) {
   return AMUSE_OK;
 }
 int amuse_profile_read(amuse_ctx* ctx, int64_t* stamps, int n) {
-  if (!ctx || !stamps || n < 1 || n > 256) return fail(ctx, AMUSE_E_INVALID, "bad argument");
+  if (!ctx || !stamps || n < 1 || n > 512) return fail(ctx, AMUSE_E_INVALID, "bad argument");
   cudaSetDevice(ctx->device);
   CU(cudaMemcpy(stamps, ctx->d_prof, sizeof(long long) * n, cudaMemcpyDeviceToHost));
   return AMUSE_OK;

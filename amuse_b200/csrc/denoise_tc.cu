@@ -61,6 +61,8 @@ constexpr int kRows = kTMax;
 constexpr int kNR = 3;                            // rows per thread in the row-split (K-split) epilogues: group 0 rows 0..2, group 1 rows 3..4
 constexpr uint32_t kSlotCols = 128, kSlots = 3;
 constexpr uint32_t kColD = kSlots * kSlotCols;   // accumulator i in columns [kColD + 32 i, +32)
+constexpr uint32_t kColSide = kColD + 64;        // two 32-column side slots for the out_proj tiles (K = 32): they do not
+                                                 // occupy a 128-column ring slot, so the ring runs one big tile further ahead
 constexpr int kTmemCols = 512;
 __host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {   // cute::UMMA::InstrDescriptor: D = F32, A = B = F16, K-major
   return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
@@ -100,11 +102,13 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d, uint32_t a, uint64_t b, 
       "r"(a), "l"(b), "r"(idesc), "r"(acc)
       : "memory");
 }
-__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+// streaming 16-B load at base + OFF bytes (immediate offset: one address register pair serves all loads of a tile)
+template <int OFF>
+__device__ __forceinline__ uint4 ldg_stream(const uint4* base) {
   uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4+%5];"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-               : "l"(p));
+               : "l"(base), "n"(OFF));
   return v;
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint4 (&r)[4]) {
@@ -165,69 +169,137 @@ struct Ctx {
   __device__ __forceinline__ uint64_t* dbar(int i) const { return bars + 6 + i; }
   __device__ __forceinline__ uint64_t* xbar(uint32_t i) const { return bars + 8 + i; }
   __device__ __forceinline__ uint64_t* bready() const { return bars + 10; }
+  __device__ __forceinline__ uint64_t* sfull(int i) const { return bars + 11 + i; }    // side slots: the two out_proj tiles
+  __device__ __forceinline__ uint64_t* sempty(int i) const { return bars + 13 + i; }
 };
-// mbarrier wait.  try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or ~10 us
-// pass) instead of re-issuing the probe -- 17 warps spin-polling mbarriers saturated the SM's shared-memory pipe and
-// made every shuffle / LDS of the epilogue warps 3-4x slower (LayerNorm 1500 cycles, measured).
-// Bounded: a protocol bug must end the launch (trap -> the host sees a launch failure), never hang the GPU.
-__device__ __forceinline__ bool try_wait_hint(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(10000u)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void wait_bar(const Ctx& k, uint64_t* bar, uint32_t parity) {
-  for (uint32_t i = 0; i < (1u << 20); ++i)
-    if (try_wait_hint(bar, parity)) return;
+// mbarrier wait (plain try_wait: the warp is suspended by the hardware for a bounded time per probe.  A suspend-time
+// hint is NOT used: ptxas turns it into try_wait + NANOSLEEP(hint) + re-check, which added microseconds to every
+// producer hand-off -- measured).  Bounded: a protocol bug must end the launch (trap -> the host sees a launch
+// failure), never hang the GPU.
+__device__ __forceinline__ void wait_timeout(const Ctx& k) {
   if (k.status) *k.status = 1;
   __trap();
 }
+// 4 instructions per probe (the C++ loop around mbar_try_wait compiled to 8, and the probes of the waiting warps are a
+// visible share of all issued instructions: profiles/r02_denoise_tc_lines.txt)
+__device__ __forceinline__ void wait_bar(const Ctx& k, uint64_t* bar, uint32_t parity) {
+  uint32_t expired;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .u32 c;\n\t"
+      "mov.u32 c, 0;\n"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "add.u32 c, c, 1;\n\t"
+      "setp.lt.u32 p, c, 16777216;\n\t"
+      "@p bra WAIT_%=;\n\t"
+      "mov.u32 %0, 1;\n\t"
+      "bra END_%=;\n"
+      "DONE_%=:\n\t"
+      "mov.u32 %0, 0;\n"
+      "END_%=:\n\t}"
+      : "=r"(expired)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  if (expired) wait_timeout(k);
+}
+
+// a wait that is not on the critical path (the producers run ahead of the MMAs): sleep between probes
+__device__ __forceinline__ void wait_bar_relaxed(const Ctx& k, uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
+  for (uint32_t i = 0; i < (1u << 22); ++i) {
+    if (mbar_try_wait(bar, parity)) return;
+    __nanosleep(100);
+  }
+  wait_timeout(k);
+}
 
 // ---------------------------------------------------------------- weight producers (8 warps)
-// Tile g (global sequence number: stage-major, rank 2r then 2r+1) goes to TMEM slot g % 3.  Each warp owns one TMEM
-// lane quadrant (32 features) and every second 16-column unit of the tile: 4 x LDG.128 per unit and thread (512
-// contiguous bytes per warp instruction), all units of a tile in flight at once, then tcgen05.st.x16 per unit.
-__device__ void producer_loop(const Ctx& k, int pw, int lane, uint32_t rank) {
+// The CTA's weight stream is one linear sequence of tiles (stage-major, rank 2r then 2r+1); tile g goes to TMEM slot
+// g % 3.  Each warp owns one TMEM lane quadrant (32 features) and every second 16-column unit of the tile: 4 x LDG.128
+// per unit and thread (512 contiguous bytes per warp instruction), all of the warp's units of a tile in flight at once,
+// then one tcgen05.st.x16 per unit.  Straight-line code per tile shape: the first version (one generic predicated loop)
+// executed ~200 instructions per warp and tile, a third of everything the SM issued (profiles/r02_denoise_tc_lines.txt).
+template <int UNITS, int QUADS>   // UNITS = my units in the tile, QUADS = feature quadrants stored
+__device__ __forceinline__ void produce_tile(const Ctx& k, const uint4* src, int q, int grp, uint32_t dst, uint64_t* empty_bar,
+                                             uint32_t empty_parity, bool wait_empty) {
+  if (q >= QUADS) {   // the q|k|v tile has 96 features: nothing for the warps of the fourth quadrant
+    if (wait_empty) wait_bar_relaxed(k, empty_bar, empty_parity);
+    return;
+  }
+  constexpr int S = 2 * QUADS * 128 * 16;   // bytes between two of my units
+  const uint4* s = src + (grp * QUADS + q) * 128;
+  uint4 a[4], b[4], c[4], d[4];
+#define DN2_LOAD(R, J)                           \
+  R[0] = ldg_stream<(J) * S>(s);                 \
+  R[1] = ldg_stream<(J) * S + 512>(s);           \
+  R[2] = ldg_stream<(J) * S + 1024>(s);          \
+  R[3] = ldg_stream<(J) * S + 1536>(s);
+  DN2_LOAD(a, 0)
+  if constexpr (UNITS > 1) { DN2_LOAD(b, 1) }
+  if constexpr (UNITS > 2) { DN2_LOAD(c, 2) DN2_LOAD(d, 3) }
+#undef DN2_LOAD
+  if (wait_empty) wait_bar_relaxed(k, empty_bar, empty_parity);   // the MMAs on the previous occupant are complete
+  tc_fence_after();
+  tmem_st16(dst + grp * 16, a);
+  if constexpr (UNITS > 1) tmem_st16(dst + (grp + 2) * 16, b);
+  if constexpr (UNITS > 2) {
+    tmem_st16(dst + (grp + 4) * 16, c);
+    tmem_st16(dst + (grp + 6) * 16, d);
+  }
+}
+__device__ __forceinline__ void producer_loop(const Ctx& k, int pw, int lane, uint32_t rank) {
   const int q = pw & 3, grp = pw >> 2;
   const uint32_t lane_base = k.tmem + (static_cast<uint32_t>(q * 32) << 16);
-  const uint4* src0 = k.p->blob + static_cast<size_t>(rank * kVirt) * kRankVec4 + lane;
-  const uint32_t total = static_cast<uint32_t>(k.p->n_steps) * kTilesPerStep * kVirt;
-  uint32_t stage = 0, slot = 0, use = 0;   // stage in step, slot = g % 3, use = g / 3
-  for (uint32_t g = 0; g < total; ++g) {
-    const int2 ti = c_tiles[stage];
-    const int kind = ti.x;
-    const int quads = (kind == kQKV) ? 3 : 4;
-    const int mine = ((kind == kWO) ? 2 : (kind == kSK) ? 4 : 8) >> 1;   // my units: grp, grp + 2, ...
-    const bool has = (q < quads) && !(k.p->debug_flags & 1);
-    const uint4* src = src0 + (g & 1) * kRankVec4 + ti.y;
-    uint4 r[4][4];
+  const uint4* const src0 = k.p->blob + static_cast<size_t>(rank) * (kVirt * kRankVec4) + lane;
+  const bool off = (k.p->debug_flags & 1) != 0;
+  uint32_t slot = 0, use = 0;   // ring slot and use count of the next ring tile
+  uint32_t suse = 0;            // use count of the side slots
+  for (int step = 0; step < k.p->n_steps; ++step) {
+    const uint4* src = src0;
+    for (int stage = 0; stage < kTilesPerStep; ++stage) {
+      const int kind = c_tiles[stage].x;
+      if (kind == kWO) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (has && j < mine) {
-        const uint4* s = src + ((grp + 2 * j) * quads + q) * 128;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) r[j][i] = ldg_stream(s + i * 32);
+        for (int t = 0; t < kVirt; ++t) {
+          if (off) {
+            if (suse > 0) wait_bar_relaxed(k, k.sempty(t), (suse - 1) & 1);
+          } else {
+            produce_tile<1, 4>(k, src, q, grp, lane_base + kColSide + t * 32, k.sempty(t), (suse - 1) & 1, suse > 0);
+          }
+          src += tile_vec4(kWO);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(k.sfull(t));
+        }
+        ++suse;
+        continue;
       }
-    if (use > 0) wait_bar(k, k.empty(slot), (use - 1) & 1);   // the MMAs on the previous occupant are complete
-    tc_fence_after();
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (has && j < mine) tmem_st16(lane_base + slot * kSlotCols + (grp + 2 * j) * 16, r[j]);
-    tmem_st_wait();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(k.full(slot));
-    if (g & 1) {
-      if (++stage == kTilesPerStep) stage = 0;
-    }
-    if (++slot == kSlots) {
-      slot = 0;
-      ++use;
+      for (int t = 0; t < kVirt; ++t) {
+        const uint32_t dst = lane_base + slot * kSlotCols;
+        const bool we = use > 0;
+        const uint32_t par = (use - 1) & 1;
+        if (off) {
+          if (we) wait_bar_relaxed(k, k.empty(slot), par);
+        } else if (kind == kQKV) {
+          produce_tile<4, 3>(k, src, q, grp, dst, k.empty(slot), par, we);
+        } else if (kind == kSK) {
+          produce_tile<2, 4>(k, src, q, grp, dst, k.empty(slot), par, we);
+        } else {
+          produce_tile<4, 4>(k, src, q, grp, dst, k.empty(slot), par, we);
+        }
+        src += (kind == kQKV) ? tile_vec4(kQKV) : (kind == kSK) ? tile_vec4(kSK) : tile_vec4(kW1);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(k.full(slot));
+        if (++slot == kSlots) {
+          slot = 0;
+          ++use;
+        }
+      }
     }
   }
 }
@@ -243,12 +315,12 @@ __device__ __forceinline__ void issue_tile(uint32_t a, uint32_t d, uint64_t bdes
     umma_f16_ts(d + 16, a + K / 2 + kk * 8, bd, kIdescN16, 1u);            // W_lo' . x_hi
   }
 }
-__device__ void issuer_loop(const Ctx& k) {
+__device__ __forceinline__ void issuer_loop(const Ctx& k) {
   const Params& p = *k.p;
   const bool prof_cta = (p.prof != nullptr) && cluster_id_x() == 0 && cluster_ctarank() == 0;
   const uint64_t dBx = umma_desc(smem_u32(k.smem + oBx)), dBo = umma_desc(smem_u32(k.smem + oBo)),
                  dBh = umma_desc(smem_u32(k.smem + oBh));
-  uint32_t slot = 0, use = 0, bph = 0;
+  uint32_t slot = 0, use = 0, suse = 0, bph = 0;
   for (int step = 0; step < p.n_steps; ++step) {
     for (int stage = 0; stage < kTilesPerStep; ++stage) {
       const int kind = c_tiles[stage].x;
@@ -256,13 +328,19 @@ __device__ void issuer_loop(const Ctx& k) {
       const uint64_t bdesc = (kind == kWO) ? dBo : (kind == kW2) ? dBh : dBx;
       const int ksteps = (kind == kWO) ? 2 : (kind == kSK) ? 4 : 8;
       // the stage's two weight tiles (usually long in TMEM): observed here, while the epilogue warps are still busy
+      const bool side = (kind == kWO);
       uint32_t s2 = slot + 1, u2 = use;
       if (s2 == kSlots) {
         s2 = 0;
         ++u2;
       }
-      wait_bar(k, k.full(slot), use & 1);
-      wait_bar(k, k.full(s2), u2 & 1);
+      if (side) {
+        wait_bar(k, k.sfull(0), suse & 1);
+        wait_bar(k, k.sfull(1), suse & 1);
+      } else {
+        wait_bar(k, k.full(slot), use & 1);
+        wait_bar(k, k.full(s2), u2 & 1);
+      }
       wait_bar(k, k.bready(), bph);
       bph ^= 1;
       tc_fence_after();
@@ -272,7 +350,7 @@ __device__ void issuer_loop(const Ctx& k) {
 #pragma unroll
         for (int t = 0; t < kVirt; ++t) {
           const uint32_t sl = t ? s2 : slot;
-          const uint32_t a = k.tmem + sl * kSlotCols;
+          const uint32_t a = k.tmem + (side ? kColSide + t * 32 : sl * kSlotCols);
           const uint32_t d = k.tmem + kColD + (nsplit ? t * 32 : 0);
           const int jbase = nsplit ? 0 : t * ksteps;
           const bool acc0 = !nsplit && t > 0;
@@ -281,16 +359,20 @@ __device__ void issuer_loop(const Ctx& k) {
           else issue_tile<128>(a, d, bdesc, jbase, acc0);
           if (nsplit) umma_commit(k.dbar(t));
           else if (t == kVirt - 1) umma_commit(k.dbar(0));
-          umma_commit(k.empty(sl));
+          umma_commit(side ? k.sempty(t) : k.empty(sl));
         }
       }
       __syncwarp();
       if (fine && elect_one()) p.prof[stage == 5 ? 109 : 113] = clock64();
-      slot = s2 + 1;
-      use = u2;
-      if (slot == kSlots) {
-        slot = 0;
-        ++use;
+      if (side) {
+        ++suse;
+      } else {
+        slot = s2 + 1;
+        use = u2;
+        if (slot == kSlots) {
+          slot = 0;
+          ++use;
+        }
       }
     }
   }
@@ -318,7 +400,9 @@ struct Chain {
   long long* wprof = nullptr; // debug: this warp's stamp row (lane 0 of every epilogue warp of cluster 0 / CTA 0), armed for
                               // the out_proj and FFN1 stages of layer 1 of the profiled step
   __device__ __forceinline__ void stamp(int point) const {
+#ifdef AMUSE_DN2_FINE   // developer build: per-warp timeline of two stages (scripts/quick_bench.py prints it)
     if (wprof) wprof[point] = clock64();
+#endif
   }
 
   __device__ Chain(const Ctx& k_, int q_, int t_, int lane_, uint32_t rank_)
@@ -326,6 +410,7 @@ struct Chain {
         lane_taddr(k_.tmem + (static_cast<uint32_t>(q_ * 32) << 16)) {}
 
   __device__ __forceinline__ void bar_group() const { bar_named(2 + t); }
+  __device__ __forceinline__ void bar_all() const { asm volatile("bar.sync 1, 256;" ::: "memory"); }
   // bias | LN weight | LN bias of the stage about to run, for weight rank 2 rank + v
   __device__ __forceinline__ const float* vec(int v) const {
     return k.p->vecs + static_cast<size_t>(rank * kVirt + v) * kRankVecFloats + g_tile * 384 + f;
@@ -355,20 +440,17 @@ struct Chain {
     __syncwarp();
     if (lane == 0) mbar_arrive(k.bready());
   }
-  // N-split stage: the accumulator of my group's tile, all 5 rows
-  __device__ __forceinline__ void gemm_nsplit(float (&y)[kRows]) {
-    stamp(9);
-    signal_b();
-    wait_bar(k, k.dbar(t), t ? dph1 : dph0);
-    stamp(10);
-    dph0 ^= 1;
-    dph1 ^= 1;
-    ++g_tile;
+  // N-split stage: accumulator i (the tile of weight rank 2 rank + i) as soon as ITS MMAs have committed, my group's rows;
+  // the epilogue of tile 0 runs under the MMAs of tile 1
+  __device__ __forceinline__ void acc_nsplit(int i, float (&y)[kNR]) {
+    wait_bar(k, k.dbar(i), i ? dph1 : dph0);
+    if (i) dph1 ^= 1;
+    else dph0 ^= 1;
     tc_fence_after();
     float a[8], b[8];
-    tmem_ld_2x8(lane_taddr + kColD + t * 32, a, b);
+    tmem_ld_2x8(lane_taddr + kColD + i * 32, a, b);
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) y[r] = fmaf(b[r], 1.0f / 2048.0f, a[r]);
+    for (int j = 0; j < kNR; ++j) y[j] = t ? fmaf(b[3 + j], 1.0f / 2048.0f, a[3 + j]) : fmaf(b[j], 1.0f / 2048.0f, a[j]);
   }
   // K-split stage: one accumulator (the sum over my two ranks), my group's rows
   __device__ __forceinline__ void gemm_ksplit(float (&y)[kNR]) {
@@ -544,7 +626,6 @@ __device__ void Chain::run() {
   const int T = p.T;
   const int clip = static_cast<int>(cluster_id_x());
   const bool do_prof_chain = (p.prof != nullptr) && clip == 0 && rank == 0 && t == 0 && f == 0;
-  float* const QKVs = reinterpret_cast<float*>(smem + oQKV) + t * (kRows * kQkvLd);
   float* const SK = reinterpret_cast<float*>(smem + oSK);
   const int row0 = t * kNR, nr = t ? 2 : 3;   // my rows in the row-split epilogues
 
@@ -611,15 +692,22 @@ __device__ void Chain::run() {
 
       // =============== QKV of head 2 rank + t (nn.MultiheadAttention in_proj; q scaled by head_dim^-0.5 after the bias)
       {
-        float y[kRows];
-        const float bias = __ldg(vec(t));
-        gemm_nsplit(y);
-        if (f < 96) {
-          const float sc = (q == 0) ? 0.17677669529663687f : 1.0f;
+        float y[kNR];
+        const float b0 = __ldg(vec(0)), b1 = __ldg(vec(1));
+        const float sc = (q == 0) ? 0.17677669529663687f : 1.0f;
+        float* const Q0 = reinterpret_cast<float*>(smem + oQKV) + row0 * kQkvLd + f;
+        signal_b();
 #pragma unroll
-          for (int r = 0; r < kRows; ++r) QKVs[r * kQkvLd + f] = (y[r] + bias) * sc;
+        for (int i = 0; i < kVirt; ++i) {
+          acc_nsplit(i, y);
+          if (f < 96) {
+#pragma unroll
+            for (int j = 0; j < kNR; ++j)
+              if (j < nr) Q0[(i * kRows + j) * kQkvLd] = (y[j] + (i ? b1 : b0)) * sc;
+          }
         }
-        bar_group();
+        ++g_tile;
+        bar_all();
       }
       DN2_PROF(2 + layer * 10 + 1);
       attention(T);
@@ -652,16 +740,17 @@ __device__ void Chain::run() {
 
       // =============== FFN1: hidden slice 2 rank + t, erf-GELU
       {
-        float y[kRows];
-        const float bias = __ldg(vec(t));
-        gemm_nsplit(y);
-        stamp(11);
+        float y[kNR];
+        const float b0 = __ldg(vec(0)), b1 = __ldg(vec(1));
+        signal_b();
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) y[r] = gelu_erf(y[r] + bias);
-        asm volatile("" ::"f"(y[0]), "f"(y[1]), "f"(y[2]), "f"(y[3]), "f"(y[4]));
-        stamp(12);
-        write_b(oBh, t * 128 + f, 0, y, kRows);
-        stamp(13);
+        for (int i = 0; i < kVirt; ++i) {
+          acc_nsplit(i, y);
+#pragma unroll
+          for (int j = 0; j < kNR; ++j) y[j] = gelu_erf(y[j] + (i ? b1 : b0));
+          write_b(oBh, i * 128 + f, row0, y, nr);
+        }
+        ++g_tile;
         wprof = nullptr;
       }
       DN2_PROF(2 + layer * 10 + 5);
@@ -749,6 +838,10 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     mbar_init(k.xbar(0), 1);
     mbar_init(k.xbar(1), 1);
     mbar_init(k.bready(), kChainWarps);
+    for (int i = 0; i < kVirt; ++i) {
+      mbar_init(k.sfull(i), kProdWarps);
+      mbar_init(k.sempty(i), 1);
+    }
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc<kTmemCols>(tmem_slot);
@@ -759,11 +852,13 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   cluster_sync_all();   // both CTAs are resident, zero-filled and have their mbarriers initialised before either
                         // stores into the other's shared memory
 
-  if (warp < kChainWarps) {
-    Chain ch(k, warp & 3, warp >> 2, lane, rank);
+  // warp ids: producers 0..7, epilogue warps 8..15, issuer 16 -- the warp scheduler prefers the highest id among the
+  // eligible warps, and the producers are the one role that is never on the critical path
+  if (warp < kProdWarps) {
+    producer_loop(k, warp, lane, rank);
+  } else if (warp < kProdWarps + kChainWarps) {
+    Chain ch(k, warp & 3, (warp - kProdWarps) >> 2, lane, rank);
     ch.run();
-  } else if (warp < kChainWarps + kProdWarps) {
-    producer_loop(k, warp - kChainWarps, lane, rank);
   } else {
     issuer_loop(k);
   }

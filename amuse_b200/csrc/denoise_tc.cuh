@@ -55,7 +55,7 @@ __host__ __device__ inline void tile_info(int i, int& kind, int& off_vec4) {
 }
 
 struct Params {
-  const uint4* blob;         // [kRanks][kRankVec4]
+  const uint4* blob;         // [kCluster][40 stages][kVirt] tiles: each CTA's two rank streams interleaved in consumption order
   const float* vecs;         // [kRanks][kRankVecFloats]
   const float* temb;         // [n_steps][128]   time tokens (a3), batch-invariant
   const float* cond;         // [B][3][128]      condition tokens + their PE rows (a4+a5); first T-2 valid

@@ -49,7 +49,7 @@ def main():
     # in-kernel cycle stamps of step 3
     eng.profile_arm(3)
     eng.denoise(l0, con, emo, sty, n_steps=8)
-    st = eng.profile_read(256)
+    st = eng.profile_read(512)
     names = ["skip", "qkv", "attn", "oproj+wait", "sum+ln1", "ffn1", "ffn2+wait", "sum+ln2"]
     print("step cycles total:", st[92] - st[0], " build-x:", st[1] - st[0])
     for l in range(9):
@@ -62,16 +62,16 @@ def main():
     print("final+update:", st[92] - st[2 + 8 * 10 + 7])
     if not st[128]:
         print("layer0 exchange waits: out_proj", st[5] - st[105], " ffn2", st[8] - st[108])
-    if len(st) >= 256 and st[128]:   # tensor-core kernel: per-warp stamps inside the out_proj and FFN1 stages of layer 1
+    if len(st) >= 512 and st[128]:   # tensor-core kernel: per-warp stamps inside the out_proj and FFN1 stages of layer 1
         t0 = st[128]
         iss = [st[108] - t0, st[109] - t0, st[112] - t0, st[113] - t0]
         print(f"issuer (relative to warp 0 entering out_proj): bready {iss[0]} issued {iss[1]} | ffn1: bready {iss[2]} issued {iss[3]}")
         names = ["start", "mma-done", "drained", "sent", "recvd", "ln-pre-bar", "ln-post-bar", "ln-done", "b-written",
-                 "ffn1-start", "ffn1-mma-done", "ffn1-drained", "gelu-done", "ffn1-b-written"]
-        print("warp(t,q) " + " ".join(f"{n:>13}" for n in names))
-        for w in range(8):
+                 "ffn1-start", "ffn1-d0", "ffn1-gelu0", "ffn1-d1", "ffn1-gelu1"]
+        print("warp(r,q) " + " ".join(f"{n:>11}" for n in names))
+        for w in range(20):
             row = st[128 + w * 16: 128 + w * 16 + 14]
-            print(f"   ({w >> 2},{w & 3})  " + " ".join(f"{v - t0:13d}" for v in row))
+            print(f"   ({w >> 2},{w & 3})  " + " ".join(f"{v - t0:11d}" for v in row))
     elif st[112]:   # library built with -DAMUSE_FINE_PROF: inside the stages of layer 1 (thread 0)
         print(f"fine qkv : acquire={st[120] - st[12]} gemm={st[121] - st[120]} park+sync={st[122] - st[121]} "
               f"gather={st[123] - st[122]} sync={st[13] - st[123]}")
