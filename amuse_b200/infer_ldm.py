@@ -33,14 +33,14 @@ _TAKES = {
 
 
 def mapinfo2takes(info, trainer=False):
-    """``[ayana-scott]_[fear]`` -> the two take ids of that emotion (reference infer_ldm.py:519-527).
-    Returns None when no emotion name occurs, like the reference's fall-through."""
+    """``[ayana-scott]_[fear]`` -> the two take ids of that emotion (reference infer_ldm.py:519-528).
+    Raises ``Exception("Unknown emotion: ", info)`` when no emotion name occurs, like the reference."""
     if not trainer:
         info = info.split("_")[1]
     for emotion in ("happy", "sad", "angry", "contempt", "disgust", "surprise", "fear"):   # reference test order
         if emotion in info:
             return _TAKES[emotion]
-    return None
+    raise Exception("Unknown emotion: ", info)
 
 
 def _first_int(s: str) -> int:
@@ -103,8 +103,8 @@ class PretrainedLPDM_v1:
         self.target_length, self.norm_mean, self.norm_std = wav["target_length"], wav["dataset_mean"], wav["dataset_std"]
         self.num_mel_bins = wav["num_mel_bins"]
         self.seq_len = self.train_pose_framelen
-        if self.smplx_rep != "6D" or self.skip_trans or self.train_upper_body or not self.smplx_data:
-            raise NotImplementedError("amuse_b200 implements the released configuration: SMPL-X 6D, full body, with trans")
+        if self.smplx_rep not in ("6D", "3D") or self.skip_trans or self.train_upper_body or not self.smplx_data:
+            raise NotImplementedError("amuse_b200 implements the released configuration: SMPL-X 6D (or 3D), full body, with trans")
         if self.seq_len != 300:
             raise NotImplementedError("amuse_b200 is built for train_pose_framelen = 300")
 
@@ -159,9 +159,14 @@ class PretrainedLPDM_v1:
         audio_ablation = config["TRAIN_PARAM"]["wav_dtw_mfcc"].get("ablation")
         assert audio_ablation is not None, f"[LPDM EVAL] Audio ablation flag: {audio_ablation}"
         ast_dir = root / "saved-models" / config["TRAIN_PARAM"][self.tag]["pretrained_ast"]
-        if ast_dir.is_dir():
-            ast_sd = torch.load(self._pick_ast(ast_dir, audio_ablation), map_location="cpu")
+        if not ast_dir.is_dir():    # the reference iterates the directory in setup (infer_pretrained_ast_evp.py:16) and raises
+            raise FileNotFoundError(f"pretrained AST directory {ast_dir} does not exist")
+        ast_sd = torch.load(self._pick_ast(ast_dir, audio_ablation), map_location="cpu")
         self.frame_based_feats = config["TRAIN_PARAM"]["wav_dtw_mfcc"]["frame_based_feats"]
+        if not self.frame_based_feats:
+            # audio_main_new.py:192-201: frame_based_feats False pools (cls + dist) / 2 instead of the mean over the patch
+            # tokens; the engine's AST kernels implement the released (True) pooling only
+            raise NotImplementedError("wav_dtw_mfcc.frame_based_feats = false (cls/dist pooling) is not implemented")
         self._load_engine(den_sd, vae_sd, ast_sd)
         return ldm_epoch
 
@@ -226,7 +231,11 @@ class PretrainedLPDM_v1:
         with torch.no_grad():
             out = self.engine.diffusion_backward(latents.view(bsz, -1), z_con, z_emo, z_sty,
                                                  n_steps=self.num_inference_timesteps, sampler=self.sampler,
-                                                 eta=float(self.eta), seed=seed)
+                                                 eta=float(self.eta), seed=seed, want_feats=self.smplx_rep != "6D")
+        if self.smplx_rep != "6D":
+            # infer_ldm.py:175-177: the decoder's features ARE the pose vector: [b, t, (j 3) | trans], no rotation conversion
+            feats = out["feats"]
+            return {"poses": feats[:, :, :-3].reshape(bsz, feats.shape[1], -1, 3), "trans": feats[:, :, -3:]}
         return {"poses": out["poses"], "trans": out["trans"]}
 
     # ------------------------------------------------------------------ audio (infer_ldm.py:180-193)
@@ -256,6 +265,10 @@ class PretrainedLPDM_v1:
         return con, emo, sty
 
     def collect_audio_metrics(self, sliced_chunk, framerate=16000 // 2, baseline=False, tgtpath=None):
+        """Deliberately unsupported: the reference's version (infer_ldm.py:195-208) dumps the
+        filterbank RECONSTRUCTED by AST_EVP's fusion + decoder heads (``eval_func(..., metrics=True)``), a training
+        diagnostic of the audio auto-encoder that no caller in scripts/trainer.py uses and that is not on the
+        gesture-sampling path; the engine does not load those heads."""
         raise NotImplementedError("fbank reconstruction metrics (AST_EVP fusion/decoder heads) are outside the sampling path")
 
     # ------------------------------------------------------------------ edits (infer_ldm.py:225-517)

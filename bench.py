@@ -12,8 +12,11 @@ Metric: SMPL-X pose frames/s = n_gpus * B * 300 / seconds-per-step (weak scaling
 
 One JSON line on stdout (rank 0).  `value` = device-resident inputs; `e2e` = the same call through
 the host-buffer C-ABI entry point (amuse_diffusion_backward_host: H2D of features/noise seed,
-D2H of poses inside the timed region); `roofline` = the dominant kernel (denoise_loop_kernel);
-`cpu_baseline` = the CPU oracle port (reference algorithm in PyTorch) on the host cores.
+D2H of poses inside the timed region); `roofline` = the dominant kernel (denoise_tc_kernel, the
+tcgen05 sampler loop); `cpu_baseline` = the CPU oracle port (reference algorithm in PyTorch) on the
+host cores, a bounded sample; `--impl reference` times that port on the FULL workload, one whole
+1000-step sampling + decode per step, no extrapolation.  `config2` / `config5` are the other
+BASELINE.json configurations (B = 1 latency; the edit batch) timed the same way.
 """
 from __future__ import annotations
 
@@ -39,11 +42,17 @@ FLOP_DENOISE_PER_CLIP_STEP = 19.219e6      # BASELINE.md section 3 (2*M*N*K of e
 FLOP_DECODE_PER_CLIP = 1.7595e9
 FLOP_AST_PER_CLIP = 783.08e9               # 3 branches x 261.03 GFLOP
 AUDIO_SAMPLES = 160000                     # 10 s at 16 kHz
-# dram__bytes_read.sum + dram__bytes_write.sum of one denoise_loop_kernel launch (ncu --set full,
-# profiles/r01_denoise_loop_full.txt): the 8.77 MB of repacked weights are read from HBM once per launch and
-# served from L2 for every later step; activations never leave shared memory (0 B written).
-DENOISE_LOOP_DRAM_BYTES = 8049152
+# dram__bytes_read.sum + dram__bytes_write.sum of one denoise_tc_kernel launch (ncu --set full,
+# profiles/r02_denoise_tc_full.txt): the 7.6 MB of fp16 hi/lo' weight planes are read from HBM once per launch and
+# served from L2 for every later step; activations never leave shared / tensor memory.
+DENOISE_LOOP_DRAM_BYTES = 7932416
 METRIC = "SMPL-X pose frames/sec over full DDPM sampling (10 s clip, batch 64)"
+
+
+def workload_name(B):
+    """config.workload -- the SAME string in both arms (the driver compares them)."""
+    return (f"diffusion_backward: B={B}/GPU synthetic 10 s clips, {SAMPLER} {N_STEPS} steps -> MotionPrior.decode -> "
+            "6D->axis-angle poses")
 
 
 def log(*a):
@@ -155,42 +164,35 @@ def cpu_reference_step(den, vae, B, n_steps, sampler, seed=0):
 
 
 def run_reference(args, rank, world):
-    """`--impl reference`: the reference's CPU algorithm (oracle port; /root/reference does not exist on
-    the GPU box) on all host threads; each step = the full B=64 x 1000-step workload."""
+    """`--impl reference`: the reference's CPU algorithm (oracle port, pinned to the reference's own modules at 2-3e-6;
+    /root/reference itself cannot travel to the GPU box) on the host threads that serve it best.  Each step is the
+    WHOLE workload of the CUDA arm's step -- 64 clips per GPU of the run x 1000 ancestral steps + decode + rotation
+    conversion -- measured, not extrapolated.  Rank 0 alone runs it."""
     if rank != 0:
         return
     from oracle import weights as W
     den, vae = W.denoiser_state_dict(), W.motionprior_state_dict()
-    B = B_PER_GPU
-    pick_cpu_threads(den, B)
-    sample_steps = 100                    # bounded sample: 100 of the 1000 denoiser steps + one full decode
+    B = B_PER_GPU * world
+    pick_cpu_threads(den, B_PER_GPU)
     for _ in range(args.warmup):
-        cpu_reference_step(den, vae, B, 10, SAMPLER)
+        cpu_reference_step(den, vae, B, N_STEPS, SAMPLER)
     ts = []
     for _ in range(args.steps):
-        dt_s, _ = cpu_reference_step(den, vae, B, sample_steps, SAMPLER)
+        dt_s, _ = cpu_reference_step(den, vae, B, N_STEPS, SAMPLER)
         ts.append(dt_s)
-    # extrapolate the denoise part linearly to 1000 steps; the decode part is measured whole
-    from oracle import lpdm_ref as R
-    z = torch.randn(B, 128)
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        R.feats_to_motion(R.vae_decode(vae, z))
-    t_dec = time.perf_counter() - t0
-    t_sample = sum(ts) / len(ts)
-    t_full = (t_sample - t_dec) * (N_STEPS / sample_steps) + t_dec
+    t_full = sum(ts) / len(ts)
     value = B * FRAMES / t_full
     cores = torch.get_num_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_full * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"diffusion_backward B={B} {SAMPLER}{N_STEPS} + decode + 6D->axis-angle (CPU oracle port)",
-                   "global_batch": B, "sampler": SAMPLER, "n_steps": N_STEPS},
+        "config": {"workload": workload_name(B_PER_GPU), "global_batch": B, "sampler": SAMPLER, "n_steps": N_STEPS,
+                   "parallelism": f"dp{world} (clip shards, no in-loop collective)",
+                   "arm": "CPU oracle port of the reference algorithm (PyTorch fp32), the whole global batch on one host"},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"B={B}: {sample_steps} of {N_STEPS} denoiser steps timed and scaled x{N_STEPS // sample_steps}, "
-                                   f"plus one full decode + rotation conversion; thread count auto-picked from a probe "
-                                   f"(host has {os.cpu_count()} logical CPUs)"},
+                         "sample": f"none: every timed step is the full B={B} x {N_STEPS}-step sampling + decode + rotation "
+                                   f"conversion; thread count auto-picked from a probe (host has {os.cpu_count()} logical CPUs)"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -205,14 +207,15 @@ def run_ours(args, rank, world, local_rank):
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    from amuse_b200 import shard
     # rank 0 draws the weights; NCCL broadcast to the other ranks (north_star: broadcast at init)
     den, vae = W.denoiser_state_dict(), W.motionprior_state_dict()
     if world > 1:
         for sd in (den, vae):
-            for k in sd:
-                t = sd[k].to(dev) if rank == 0 else torch.empty_like(sd[k], device=dev)
-                dist.broadcast(t, src=0)
-                sd[k] = t
+            if rank != 0:
+                for k in sd:
+                    sd[k] = torch.empty_like(sd[k])
+            shard.broadcast_state_dict(sd, src=0, device=dev)
     eng = Engine(dev)
     eng.load_state_dict("denoiser", den)
     eng.load_state_dict("vae", vae)
@@ -222,7 +225,8 @@ def run_ours(args, rank, world, local_rank):
 
     # rank-0-generated inputs for the GLOBAL batch, sharded contiguously (GPU-count-invariant results)
     gl0, gcon, gemo, gsty = synth_inputs(B * world)
-    sl = slice(rank * B, (rank + 1) * B)
+    c0, c1 = shard.shard_range(B * world, rank, world)     # my clips; c0 is also my Philox clip offset
+    sl = slice(c0, c1)
     h = [t[sl].contiguous().pin_memory() for t in (gl0, gcon, gemo, gsty)]
     d = [t.to(dev) for t in h]
     seed = 1234
@@ -239,10 +243,13 @@ def run_ours(args, rank, world, local_rank):
     def dev_step(ev=None):
         if ev:
             ev[0].record()
-        z = eng.denoise(d[0], d[1], d[2], d[3], n_steps=N_STEPS, sampler=SAMPLER, seed=seed)
+        z = eng.denoise(d[0], d[1], d[2], d[3], n_steps=N_STEPS, sampler=SAMPLER, seed=seed, clip_offset=c0)
         if ev:
             ev[1].record()
         poses, trans = eng.decode(z)
+        if world > 1:        # the gather of the poses to rank 0 is part of the step (north_star: gather at the end)
+            poses = shard.gather_clips(poses, B * world, dst=0)
+            trans = shard.gather_clips(trans, B * world, dst=0)
         if ev:
             ev[2].record()
         return poses
@@ -251,7 +258,7 @@ def run_ours(args, rank, world, local_rank):
         if ev:
             ev[0].record()
         eng.diffusion_backward_host(h[0], h[1], h[2], h[3], n_steps=N_STEPS, sampler=SAMPLER, seed=seed,
-                                    out_poses=out_poses, out_trans=out_trans)
+                                    out_poses=out_poses, out_trans=out_trans, clip_offset=c0)
         if ev:
             ev[1].record()
 
@@ -311,7 +318,7 @@ def run_ours(args, rank, world, local_rank):
             con, emo, sty = eng.ast_features(fb)
             if ev:
                 ev[2].record()
-            z = eng.denoise(d[0], con, emo, sty, n_steps=N_STEPS, sampler=SAMPLER, seed=seed)
+            z = eng.denoise(d[0], con, emo, sty, n_steps=N_STEPS, sampler=SAMPLER, seed=seed, clip_offset=c0)
             poses, trans = eng.decode(z)
             if host:
                 out_poses.copy_(poses, non_blocking=True)
@@ -355,18 +362,79 @@ def run_ours(args, rank, world, local_rank):
                                     "note": "algorithmic 783.08 GFLOP/clip; fp32-accurate 3xTF32 issues 3 TF32 MMAs per "
                                             "product, i.e. 6x the bf16 tensor time, so frac <= 1/6 by construction"}}
 
-    # one gather of the poses to rank 0 (north_star: gather at the end), timed separately
+    # ---- the gather alone, for the record (it is inside `value` / `ms_per_step` at N > 1)
     gather_ms = None
     if world > 1:
-        poses = dev_step()
-        torch.cuda.synchronize(dev)
-        bufs = [torch.empty_like(poses) for _ in range(world)] if rank == 0 else None
-        dist.gather(poses, bufs, dst=0)          # warm-up (NCCL lazy init)
+        p_loc, _ = eng.decode(eng.denoise(d[0], d[1], d[2], d[3], n_steps=2, sampler="ddim"))
+        shard.gather_clips(p_loc, B * world, dst=0)          # warm-up (NCCL lazy init)
         barrier()
-        g0 = time.perf_counter()
-        dist.gather(poses, bufs, dst=0)
+        g0 = torch.cuda.Event(enable_timing=True)
+        g1 = torch.cuda.Event(enable_timing=True)
+        g0.record()
+        shard.gather_clips(p_loc, B * world, dst=0)
+        g1.record()
         torch.cuda.synchronize(dev)
-        gather_ms = (time.perf_counter() - g0) * 1e3
+        gather_ms = g0.elapsed_time(g1)
+
+    # ---- GPU-count invariance on hardware: a small global batch, sharded over the ranks with their clip
+    #      offsets and gathered through the product's helpers, equals the same batch computed by rank 0 alone
+    nb = 3 * world + 1                                        # ragged on purpose: the first rank gets one clip more
+    sl0, sc, se, ss = synth_inputs(nb, seed_base=100)
+    a0, a1 = shard.shard_range(nb, rank, world)
+    mine = eng.diffusion_backward(sl0[a0:a1], sc[a0:a1], se[a0:a1], ss[a0:a1], n_steps=40, sampler="ddpm", seed=99,
+                                  clip_offset=a0)
+    if world > 1:
+        got = shard.gather_clips(mine["poses"], nb, dst=0)
+    else:
+        got = mine["poses"]
+    shard_check = None
+    if rank == 0:
+        whole = eng.diffusion_backward(sl0, sc, se, ss, n_steps=40, sampler="ddpm", seed=99, clip_offset=0)["poses"]
+        shard_check = {"clips": nb, "ranks": world, "sampler": "ddpm40 (in-kernel Philox)", "bit_identical": bool(torch.equal(got, whole))}
+        assert shard_check["bit_identical"], "sharded run differs from the single-GPU run of the same clips"
+
+    # ---- the other BASELINE.json configurations, timed like the headline (CUDA events, L2 flush between iterations)
+    def timed(fn, n=5):
+        fn()
+        ts = []
+        for i in range(n):
+            flush.fill_(i & 0xFF)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    peak_tf_c = load_peaks()[0]
+
+    def sub_record(Bc, n, samp, ms_loop, ms_all, what):
+        tf = Bc * n * FLOP_DENOISE_PER_CLIP_STEP / (ms_loop / 1e3) / 1e12
+        return {"what": what, "clips_per_gpu": Bc, "sampler": f"{samp}{n}", "ms": ms_all, "loop_ms": ms_loop,
+                "us_per_denoiser_step": ms_loop / n * 1e3, "value": world * Bc * FRAMES / (ms_all / 1e3), "unit": "frames/s",
+                "roofline": {"bound": "tensor", "kernel": "denoise_tc_kernel", "achieved": tf, "peak": peak_tf_c,
+                             "unit": "TFLOP/s", "frac": tf / peak_tf_c}}
+
+    config2, config5 = [], None
+    one = [t[:1].contiguous() for t in d]
+    for n, samp in ((50, "ddim"), (N_STEPS, "ddpm")):          # configs[1]: one 10 s clip, the shipped 50-step DDIM and full DDPM
+        ms_loop = timed(lambda: eng.denoise(one[0], one[1], one[2], one[3], n_steps=n, sampler=samp, seed=seed))
+        ms_all = timed(lambda: eng.diffusion_backward(one[0], one[1], one[2], one[3], n_steps=n, sampler=samp, seed=seed))
+        config2.append(sub_record(1, n, samp, ms_loop, ms_all, "configs[1]: infer_gesture, one 10 s clip (latency)"))
+    # configs[4]: edit_gesture style_Xemo_transfer, 256 triples over 8 GPUs = 32 per GPU: (con_i, emo_pi(i), sty_pi(i)) with
+    # pi the seed-4 permutation of a 256-row feature bank (the swap of infer_ldm.py:307-318)
+    bank = [torch.randn(256, 256, generator=torch.Generator().manual_seed(40 + j)) for j in range(3)]
+    perm = torch.randperm(256, generator=torch.Generator().manual_seed(4))
+    e0_, e1_ = shard.shard_range(256, rank % 8, 8)
+    idx = torch.arange(e0_, e1_)
+    econ, eemo, esty = bank[0][idx].to(dev), bank[1][perm[idx]].to(dev), bank[2][perm[idx]].to(dev)
+    el0 = torch.randn(len(idx), 128, generator=torch.Generator().manual_seed(41)).to(dev)
+    ms_loop = timed(lambda: eng.denoise(el0, econ, eemo, esty, n_steps=50, sampler="ddim"))
+    ms_all = timed(lambda: eng.diffusion_backward(el0, econ, eemo, esty, n_steps=50, sampler="ddim"))
+    config5 = sub_record(len(idx), 50, "ddim", ms_loop, ms_all,
+                         "configs[4]: edit_gesture style_Xemo_transfer, 32 (con, emo_pi, sty_pi) triples per GPU, seed-4 permutation")
 
     tt = torch.tensor([t_total, t_loop, t_dec, t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -383,13 +451,12 @@ def run_ours(args, rank, world, local_rank):
     ach_tf = flops_loop / (t_loop / K) / 1e12
     # The pipe this fp32 kernel actually runs on: FFMA2 issues every 2.75 cycles per SM sub-partition (measured,
     # scripts/ubench.cu) = 93.1 FMA/clk/SM, on the 4 SMs of every 2-clip cluster, at the SM clock sampled under load.
-    sms_used = 4 * ((B + 1) // 2)
-    sm_hz = float((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
-    fma_peak_tf = 2 * 93.1 * sms_used * sm_hz / 1e12
+    sms_used = 2 * B                                              # one clip per 2-CTA cluster
     h2d = sum(t.numel() * 4 for t in h)
     d2h = out_poses.numel() * 4 + out_trans.numel() * 4
 
-    # CPU baseline: bounded sample of the same workload on the host cores (oracle port)
+    # CPU baseline: BOUNDED SAMPLE of the same workload on the host cores (oracle port); the full, un-extrapolated
+    # measurement is the `--impl reference` arm
     den_c, vae_c = W.denoiser_state_dict(), W.motionprior_state_dict()
     cs = 100
     cpu_value = None
@@ -438,25 +505,26 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": t_total / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"diffusion_backward: B={B}/GPU synthetic 10 s clips, {SAMPLER} {N_STEPS} steps (in-kernel Philox "
-                               "noise) -> MotionPrior.decode -> 6D->axis-angle poses",
+        "config": {"workload": workload_name(B), "noise": "in-kernel Philox (stateless, keyed by global clip index)",
                    "global_batch": B * world, "sampler": SAMPLER, "n_steps": N_STEPS, "parallelism": f"dp{world} (clip shards, no in-loop collective)",
                    "l2": "256 MiB flush between timed iterations", "loop_ms": t_loop / K * 1e3, "decode_ms": t_dec / K * 1e3,
-                   "gather_ms": gather_ms},
+                   "gather_ms": gather_ms, "gather": "inside the timed step at N > 1 (amuse_b200.shard.gather_clips)",
+                   "shard_check": shard_check},
         "e2e": {"value": frames_per_step * K / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "denoise_loop_kernel", "achieved": ach_tf, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": DENOISE_LOOP_DRAM_BYTES,
-                     "fp32_fma": {"achieved": ach_tf, "peak": fma_peak_tf, "unit": "TFLOP/s", "frac": ach_tf / fma_peak_tf,
-                                  "sms_used": sms_used,
-                                  "note": "measured FFMA2 issue rate (93.1 FMA/clk/SM) x SMs holding a cluster x sampled SM clock"},
+        "roofline": {"bound": "tensor", "kernel": "denoise_tc_kernel", "achieved": ach_tf, "peak": peak_tf,
+                     "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": DENOISE_LOOP_DRAM_BYTES, "sms_used": sms_used,
                      "note": f"algorithmic 19.219 MFLOP x {B} clips x {N_STEPS} steps per launch; peak = {peak_kind} dense bf16 "
-                             "(sustained); the kernel computes in fp32 FFMA and is dependency-latency bound at 5 rows/clip"},
-        "cpu_baseline": {"value": cpu_value, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "(sustained).  Every GEMM is a tcgen05.mma (fp16 hi/lo' split, fp32-class accuracy, weights = A "
+                             "operand in TMEM); with 5 token rows per clip an MMA carries 5 of its 16/32 N columns and the step "
+                             "is a chain of 41 dependent stages, so the kernel is latency- and issue-bound, not tensor-bound"},
+        "cpu_baseline": {"value": cpu_value, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port", "sampled": True,
                          "sample": f"B={B}: {cs} of {N_STEPS} denoiser steps timed and scaled x{N_STEPS // cs}, plus one full decode; "
                                    f"thread count auto-picked from a probe (host has {os.cpu_count()} logical CPUs)"},
         "eager_gpu_baseline": eager,
+        "config2": config2,
+        "config5": config5,
         "scope_E": scope_e,
         "clocks": clocks,
     }

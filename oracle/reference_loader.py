@@ -72,3 +72,18 @@ def load_transforms():
     _stub_packages()
     import importlib
     return importlib.import_module("dm.utils.transforms")
+
+
+def load_gaussian_diffusion():
+    """The reference's vendored ``GaussianDiffusion`` module (models/diffusion/utils/mdm_gaussian_diffusion.py:181):
+    the one piece of reference-held code that contains the DDPM posterior (q_posterior_mean_variance :343-366,
+    _predict_xstart_from_eps :528) and the DDIM update (ddim_sample :895-945).  It is not on the reference's sampling
+    path (that path calls diffusers, which is not installable here) but it is the same published math, so it pins the
+    scheduler restatement in ``lpdm_ref.py``.  Imports with torch / numpy / einops only."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "_amuse_ref_gaussian_diffusion", REF / "models" / "diffusion" / "utils" / "mdm_gaussian_diffusion.py")
+    mod = importlib.util.module_from_spec(spec)
+    with contextlib.redirect_stdout(io.StringIO()):
+        spec.loader.exec_module(mod)
+    return mod

@@ -15,6 +15,19 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu`-marked tests are skipped (not failed) on a box without a CUDA device: plain `pytest tests` stays green in the
+    build container, `-m gpu` on the GPU box runs them.  A box WITH a GPU but without the built library still fails
+    loudly inside the tests (AmuseLibraryError) -- there is no fallback to skip to."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container (gpu tests run on the B200 box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN

@@ -47,7 +47,8 @@ def test_mapinfo2takes():
     assert mapinfo2takes("[ayana-scott]_[fear]") == ["0_103_103", "0_104_104"]
     assert mapinfo2takes("[yingqing]_[happy]_first") == ["0_65_65", "0_66_66"]
     assert mapinfo2takes("angry", trainer=True) == ["0_73_73", "0_74_74"]
-    assert mapinfo2takes("[a-b]_[neutral]") is None
+    with pytest.raises(Exception, match="Unknown emotion"):      # the reference's fall-through (infer_ldm.py:528)
+        mapinfo2takes("[a-b]_[neutral]")
 
 
 def test_checkpoint_selection_rules(tmp_path):
@@ -111,3 +112,19 @@ def test_shard_range():
         assert all(got[i][1] == got[i + 1][0] for i in range(w - 1))
         sizes = [b - a for a, b in got]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_setup_fixture_config_matches_the_reference_file():
+    """The configs/diff_latent_v2.json keys that tests/test_gpu_setup.py writes into its temporary tree are the released
+    file's (checked here, where /root/reference exists; the GPU box has no reference tree)."""
+    import importlib.util
+    import json
+    from oracle import reference_loader as RL
+    if not RL.available():
+        pytest.skip("/root/reference is only present in the build container")
+    spec = importlib.util.spec_from_file_location("_setup_fixture", Path(__file__).parent / "test_gpu_setup.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ref = json.loads((RL.REF / "configs" / "diff_latent_v2.json").read_text())
+    for sec in ("arch_denoiser", "noisy_scheduler", "scheduler"):
+        assert mod.LDM_CFG[sec] == ref[sec], sec

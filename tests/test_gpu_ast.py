@@ -36,6 +36,25 @@ def test_ast_features_vs_oracle(depth, B):
     eng.close()
 
 
+def test_ast_depth12_golden(golden_dir):
+    """The shipped depth (12 blocks x 3 branches, what bench.py's scope E runs) against the committed float64 output of the
+    CPU restatement for one clip (oracle/make_ast_golden.py).  Tolerance: the tensor cores accumulate with truncation,
+    so the error grows with depth; measured 4-5e-5 on |feat| ~ 3, asserted at 3e-4 like the shallow stacks."""
+    g = np.load(golden_dir / "ast_depth12_b1.npz")
+    eng, sd = _engine_with_ast(12)
+    assert W.checksum({k: sd[k] for k in list(sd)[:8]}) == str(g["weights_sha1"]), "synthetic AST weights differ from the fixture's"
+    fb = torch.randn(1, 1024, 128, generator=torch.Generator().manual_seed(int(g["fbank_seed"]))) * 0.5
+    assert torch.equal(fb[0, [0, 511, 1023], :4], torch.from_numpy(g["fbank_probe"])), "torch CPU RNG stream differs from the fixture's"
+    con, emo, sty = eng.ast_features(fb)
+    for name, got in (("con", con), ("emo", emo), ("sty", sty)):
+        ref64, ref32 = g[f"{name}_f64"], g[f"{name}_f32"]
+        e64 = np.abs(got.cpu().double().numpy() - ref64).max()
+        r = np.abs(ref32.astype(np.float64) - ref64).max()
+        print(f"[parity] ast depth=12 {name}: |cuda-f64|={e64:.3e} |f32ref-f64|={r:.3e} |feat|max={np.abs(ref64).max():.2f}")
+        assert e64 < 3e-4
+    eng.close()
+
+
 def test_process_single_seq_shapes_and_fbank():
     """The mirror class end to end on a synthetic 10 s / 16 kHz waveform: host kaldi fbank (as the
     reference), normalisation after zero padding, AST on the device."""

@@ -310,6 +310,42 @@ def test_full_size_ddpm1000_b64_properties(engine):
     assert poses.abs().max().item() <= 3.1416 + 1e-3          # axis-angle magnitude is an angle in [0, pi]
 
 
+def test_philox_path_against_oracle_full_size(engine, synthetic_weights):
+    """The benchmarked configuration itself -- B = 64, 1000 ancestral steps, noise drawn IN the kernel -- against the CPU
+    oracle: the kernel's Philox normals are exported through the debug ABI (same device function, philox.cuh), checked
+    for N(0,1) moments and stream independence, and handed to the oracle as ``step_noise``.  Tolerance as for the
+    injected-noise golden (ddpm1000_b2): within max(2e-5 |z|max, 4 x the oracle's own fp32-vs-fp64 distance) of fp64."""
+    B, n, seed = 64, 1000, 2024
+    g = torch.Generator().manual_seed(31)
+    l0, con, emo, sty = (torch.randn(B, d, generator=g) for d in (128, 256, 256, 256))
+    noise = engine.philox_normals(seed, B, n).cpu()
+    x = noise.double().flatten()
+    N = x.numel()
+    mean, var = x.mean().item(), x.var().item()
+    kurt = ((x - mean) ** 4).mean().item() / var ** 2
+    tail = (x.abs() > 3).double().mean().item()
+    print(f"[philox] N={N} mean={mean:.2e} var={var:.5f} kurtosis={kurt:.4f} P(|z|>3)={tail:.5f} max|z|={x.abs().max().item():.2f}")
+    assert abs(mean) < 4 / N ** 0.5 and abs(var - 1) < 4 * (2 / N) ** 0.5 and abs(kurt - 3) < 4 * (24 / N) ** 0.5
+    assert abs(tail - 0.0026998) < 2e-4 and x.abs().max().item() < 7.0
+    c01 = torch.corrcoef(torch.stack([noise[:, 0].flatten(), noise[:, 1].flatten()]))[0, 1].item()
+    lag = torch.corrcoef(torch.stack([noise[:-1, 0].flatten(), noise[1:, 0].flatten()]))[0, 1].item()
+    assert abs(c01) < 0.02 and abs(lag) < 0.02             # clips and consecutive steps draw independent streams
+    # the same draws through the offset argument: clips 32.. of this stream are what a second shard would see
+    assert torch.equal(engine.philox_normals(seed, 32, 4, clip_offset=32).cpu(), noise[:4, 32:])
+    got = engine.denoise(l0, con, emo, sty, n_steps=n, sampler="ddpm", seed=seed)
+    same = engine.denoise(l0, con, emo, sty, n_steps=n, sampler="ddpm", step_noise=noise)
+    assert torch.equal(got, same)                          # in-kernel draws == the exported array fed back
+    sd = synthetic_weights["denoiser"]
+    z32 = R.sample_latents(sd, l0, con, emo, sty, n, "ddpm", noise)
+    sd64 = {k: v.double() for k, v in sd.items()}
+    z64 = R.sample_latents(sd64, l0.double(), con.double(), emo.double(), sty.double(), n, "ddpm", noise.double())
+    scale = z64.abs().max().item()
+    r = (z32.double() - z64).abs().max().item()
+    e64 = (got.cpu().double() - z64).abs().max().item()
+    print(f"[parity] philox ddpm1000 B=64: CUDA vs fp64 {e64:.3e}  oracle fp32 vs fp64 {r:.3e}  |z|max {scale:.1f}")
+    assert e64 < max(2e-5 * scale, 4 * r)
+
+
 def test_empty_batch(engine):
     """bsz = 0: the reference's modules return empty tensors for an empty batch; nothing is launched here."""
     z = torch.empty(0, 256)
