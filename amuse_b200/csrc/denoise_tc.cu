@@ -83,8 +83,8 @@ constexpr int kPsSlot = 5 * 128 * 4;              // 2560
 constexpr int oPs = oBh + 16384;                  // [2 buffers][slot]
 constexpr int oQKV = oPs + 2 * kPsSlot;           // [2 heads][5][100] floats
 constexpr int oSK = oQKV + 4096;                  // [4][5][128] floats: skip stack of the input blocks
-constexpr int oStat = oSK + 4 * kRows * 128 * 4;  // [2 groups][4 warps][16] floats
-constexpr int oBars = oStat + 512;
+constexpr int oStat = oSK + 4 * kRows * 128 * 4;  // [3 buffers][2 groups][4 warps][16] floats (see Chain::layernorm)
+constexpr int oBars = oStat + 3 * 512;
 constexpr int kSmemUsed = oBars + 256;
 constexpr int kSmemBytes = 120 * 1024;            // > half of the SM's shared memory: one CTA (= one 512-column TMEM allocation) per SM
 static_assert(oBo % 1024 == 0 && oBh % 1024 == 0, "B operands must be 1024-B aligned");
@@ -223,13 +223,15 @@ __device__ __forceinline__ void wait_bar_relaxed(const Ctx& k, uint64_t* bar, ui
 template <int UNITS, int QUADS>   // UNITS = my units in the tile, QUADS = feature quadrants stored
 __device__ __forceinline__ void produce_tile(const Ctx& k, const uint4* src, int q, int grp, uint32_t dst, uint64_t* empty_bar,
                                              uint32_t empty_parity, bool wait_empty) {
+  const int dbg = k.p->debug_flags;
   if (q >= QUADS) {   // the q|k|v tile has 96 features: nothing for the warps of the fourth quadrant
     if (wait_empty) wait_bar_relaxed(k, empty_bar, empty_parity);
     return;
   }
   constexpr int S = 2 * QUADS * 128 * 16;   // bytes between two of my units
   const uint4* s = src + (grp * QUADS + q) * 128;
-  uint4 a[4], b[4], c[4], d[4];
+  uint4 a[4] = {}, b[4] = {}, c[4] = {}, d[4] = {};
+  if (!(dbg & 2)) {
 #define DN2_LOAD(R, J)                           \
   R[0] = ldg_stream<(J) * S>(s);                 \
   R[1] = ldg_stream<(J) * S + 512>(s);           \
@@ -239,8 +241,13 @@ __device__ __forceinline__ void produce_tile(const Ctx& k, const uint4* src, int
   if constexpr (UNITS > 1) { DN2_LOAD(b, 1) }
   if constexpr (UNITS > 2) { DN2_LOAD(c, 2) DN2_LOAD(d, 3) }
 #undef DN2_LOAD
+  }
   if (wait_empty) wait_bar_relaxed(k, empty_bar, empty_parity);   // the MMAs on the previous occupant are complete
   tc_fence_after();
+  if (dbg & 4) {   // timing experiment: loads only
+    asm volatile("" ::"r"(a[0].x ^ a[3].w ^ b[0].x ^ b[3].w ^ c[0].x ^ c[3].w ^ d[0].x ^ d[3].w));
+    return;
+  }
   tmem_st16(dst + grp * 16, a);
   if constexpr (UNITS > 1) tmem_st16(dst + (grp + 2) * 16, b);
   if constexpr (UNITS > 2) {
@@ -497,8 +504,13 @@ struct Chain {
   // butterfly: the xor-16 step hands the sums to the lower half-warp and the sums of squares to the upper one); lane r
   // then merges the 4 warps' (mean, M2) of row r with Chan's formula -- no cancellation whatever the row mean is --
   // and (mean, rstd) are broadcast to the warp.
+  // The moments go through one of three shared-memory buffers: LayerNorm 1 and 2 of a layer alternate between two (a
+  // warp may write the moments of the next LayerNorm while a slower warp of its group still reads the previous ones only
+  // if nothing separates the two -- every pair of consecutive LayerNorms of a layer is separated by a GEMM stage, i.e.
+  // by the bready / accumulator mbarriers, but the final encoder.norm follows LayerNorm 2 of the last layer directly:
+  // compute-sanitizer racecheck flagged exactly that write-after-read), the final norm has its own.
   template <int NR>
-  __device__ __forceinline__ void layernorm(float (&v)[kNR], float gam, float bet) const {
+  __device__ __forceinline__ void layernorm(float (&v)[kNR], float gam, float bet, int buf) const {
     float tt[NR], sh[NR];
     const bool upper = (lane & 16) != 0;
 #pragma unroll
@@ -513,7 +525,7 @@ struct Chain {
     for (int o = 8; o > 0; o >>= 1)
 #pragma unroll
       for (int r = 0; r < NR; ++r) tt[r] += __shfl_xor_sync(0xffffffffu, tt[r], o);
-    float* st = reinterpret_cast<float*>(smem + oStat) + (t * 4 + q) * 16;
+    float* st = reinterpret_cast<float*>(smem + oStat) + buf * 128 + (t * 4 + q) * 16;
     if ((lane & 15) == 0) {
 #pragma unroll
       for (int r = 0; r < NR; ++r) st[(upper ? 4 : 0) + r] = tt[r];
@@ -525,7 +537,7 @@ struct Chain {
     stamp(5);
     bar_group();
     stamp(6);
-    const float* sa = reinterpret_cast<const float*>(smem + oStat) + t * 64 + ((lane < NR) ? lane : 0);
+    const float* sa = reinterpret_cast<const float*>(smem + oStat) + buf * 128 + t * 64 + ((lane < NR) ? lane : 0);
     float mw[4], m2 = 0.f, mean = 0.f;
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
@@ -728,7 +740,7 @@ __device__ void Chain::run() {
         xchg_recv(y);
         stamp(4);
         DN2_PROF(2 + layer * 10 + 3);
-        layernorm<kNR>(y, gam, bet);
+        layernorm<kNR>(y, gam, bet, 0);
         asm volatile("" ::"f"(y[0]), "f"(y[1]), "f"(y[2]));
         stamp(7);
 #pragma unroll
@@ -766,7 +778,7 @@ __device__ void Chain::run() {
         for (int i = 0; i < kNR; ++i) y[i] += bias + x[i];
         xchg_recv(y);
         DN2_PROF(2 + layer * 10 + 6);
-        layernorm<kNR>(y, gam, bet);
+        layernorm<kNR>(y, gam, bet, 1);
 #pragma unroll
         for (int i = 0; i < kNR; ++i) x[i] = y[i];
         if (layer < 4) {
@@ -793,7 +805,7 @@ __device__ void Chain::run() {
     //      x' = c2 x0 + c3 (e | x) + sigma z
     if (t == 0) {
       float e3[kNR] = {x[0], 0.f, 0.f};
-      layernorm<1>(e3, fn_g, fn_b);
+      layernorm<1>(e3, fn_g, fn_b, 2);
       const float e = e3[0];
       float x0 = __fdiv_rn(__fsub_rn(z, __fmul_rn(coef[1], e)), coef[0]);
       if (p.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
