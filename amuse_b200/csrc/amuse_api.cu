@@ -131,6 +131,16 @@ struct amuse_ctx {
   bool dec_use_tc = true;        // decoder GEMMs on tcgen05 (3xTF32); false = fp32 FFMA kernels
   int prune_last = 1;            // denoise loop: last layer for token 0 only (AMUSE_PRUNE_LAST=0 disables; tuning hook)
   int wide_rows = 0;             // denoise loop: 10-row GEMM warps in 2-clip clusters (AMUSE_WIDE_ROWS=0/1; tuning hook)
+  // decoder pass as a CUDA graph: the ~100 launches of a 64-clip decode (each with up to 6 host-side cuTensorMapEncode
+  // calls) are captured once per (batch, buffer set) and replayed with one cudaGraphLaunch (AMUSE_DECODE_GRAPH=0 disables)
+  bool dec_graph = true;
+  struct DecGraph {
+    std::vector<uint64_t> key;
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches = 0;
+  };
+  std::vector<DecGraph> dec_graphs;
+  cudaStream_t cap_stream = nullptr;
   bool den_ffma = false;         // denoise loop on the fp32 FFMA2 kernel (denoise_loop.cu) instead of the tcgen05 one
                                  // (denoise_tc.cu): AMUSE_DENOISE_FFMA=1, A/B switch for measurements
   DevBuf h2d;   // staging for the *_host entry point
@@ -908,8 +918,8 @@ int run_decode(amuse_ctx* ctx, int B, const float* latents, float* feats6d, floa
 // the bias / q-scale / GELU / residual + LayerNorm (+ collapsed cross-attention + LayerNorm)
 // epilogues fused; activations travel between kernels as TF32 hi/lo planes (value = hi + lo).
 // Same buffer plan as run_decode: layer input cur = XB | SK[l-1] | XC, after attention XA, output SK[l] | XB.
-int run_decode_tc(amuse_ctx* ctx, int B, const float* latents, float* feats6d, float* poses, float* trans,
-                  cudaStream_t st) {
+int run_decode_tc_body(amuse_ctx* ctx, int B, const float* latents, float* feats6d, float* poses, float* trans,
+                       cudaStream_t st, bool prepare_only) {
   using namespace dec;
   DecW& d = ctx->dec;
   const float* W = d.arena.p;
@@ -937,6 +947,7 @@ int run_decode_tc(amuse_ctx* ctx, int B, const float* latents, float* feats6d, f
     CU(ctx->dZero.ensure(128));
     CU(cudaMemset(ctx->dZero.p, 0, 128 * sizeof(float)));
   }
+  if (prepare_only) return AMUSE_OK;   // every allocation / stream / event exists: the rest only enqueues work
   struct P {
     float* hi;
     float* lo;
@@ -1044,6 +1055,62 @@ int run_decode_tc(amuse_ctx* ctx, int B, const float* latents, float* feats6d, f
       CU(cudaStreamWaitEvent(caller, ctx->ev_join[i], 0));
     }
   }
+  return AMUSE_OK;
+}
+
+int run_decode_tc(amuse_ctx* ctx, int B, const float* latents, float* feats6d, float* poses, float* trans,
+                  cudaStream_t st) {
+  if (int rc = run_decode_tc_body(ctx, B, latents, feats6d, poses, trans, st, true)) return rc;
+  if (!ctx->dec_graph) return run_decode_tc_body(ctx, B, latents, feats6d, poses, trans, st, false);
+  // the graph bakes every pointer in: key = batch + plan + caller buffers + workspace / weight base addresses
+  auto u = [](const void* p) { return static_cast<uint64_t>(reinterpret_cast<uintptr_t>(p)); };
+  const std::vector<uint64_t> key = {static_cast<uint64_t>(B), static_cast<uint64_t>(ctx->dec_chunk), static_cast<uint64_t>(ctx->dec_lanes),
+                                     u(latents), u(feats6d), u(poses), u(trans), u(ctx->dec.arena.p), u(ctx->tX[0].p),
+                                     u(ctx->tX[1].p), u(ctx->tX[2].p), u(ctx->tSkip.p), u(ctx->tO.p), u(ctx->tH.p),
+                                     u(ctx->dQKV.p), u(ctx->dFeats.p), u(ctx->dCvec.p), u(ctx->dZero.p)};
+  for (auto& g : ctx->dec_graphs)
+    if (g.key == key) {
+      CU(cudaGraphLaunch(g.exec, st));
+      ctx->launches += g.launches;
+      return AMUSE_OK;
+    }
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  if (cs != cudaStreamCaptureStatusNone)   // the caller is capturing already: just enqueue into its graph
+    return run_decode_tc_body(ctx, B, latents, feats6d, poses, trans, st, false);
+  const int64_t l0 = ctx->launches;
+  // captured on a stream of our own (the caller's may be the legacy default stream, which cannot be captured); the
+  // instantiated graph is then launched on the caller's stream
+  if (!ctx->cap_stream) CU(cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking));
+  CU(cudaStreamBeginCapture(ctx->cap_stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = run_decode_tc_body(ctx, B, latents, feats6d, poses, trans, ctx->cap_stream, false);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(ctx->cap_stream, &graph);
+  if (rc != AMUSE_OK || ce != cudaSuccess) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    ctx->launches = l0;
+    if (rc != AMUSE_OK) return rc;
+    ctx->dec_graph = false;   // capture is unavailable on this stream: enqueue the launches directly from now on
+    return run_decode_tc_body(ctx, B, latents, feats6d, poses, trans, st, false);
+  }
+  amuse_ctx::DecGraph g;
+  g.key = key;
+  g.launches = ctx->launches - l0;
+  const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) {
+    cudaGetLastError();
+    ctx->dec_graph = false;
+    ctx->launches = l0;
+    return run_decode_tc_body(ctx, B, latents, feats6d, poses, trans, st, false);
+  }
+  if (ctx->dec_graphs.size() >= 8) {   // callers cycle through a handful of buffer sets at most
+    cudaGraphExecDestroy(ctx->dec_graphs.front().exec);
+    ctx->dec_graphs.erase(ctx->dec_graphs.begin());
+  }
+  ctx->dec_graphs.push_back(g);
+  CU(cudaGraphLaunch(g.exec, st));
   return AMUSE_OK;
 }
 
@@ -1193,6 +1260,7 @@ int amuse_create(amuse_ctx** out, int device_ordinal) {
   if (const char* e = getenv("AMUSE_DECODE_FFMA")) c->dec_use_tc = !(e[0] == '1');   // A/B switch for measurements
   if (const char* e = getenv("AMUSE_PRUNE_LAST")) c->prune_last = (e[0] != '0');
   if (const char* e = getenv("AMUSE_DENOISE_FFMA")) c->den_ffma = (e[0] == '1');
+  if (const char* e = getenv("AMUSE_DECODE_GRAPH")) c->dec_graph = (e[0] != '0');
   if (const char* e = getenv("AMUSE_WIDE_ROWS")) c->wide_rows = (e[0] != '0');
   if (cudaMalloc(&c->d_prof, 512 * sizeof(long long)) != cudaSuccess) {
     delete c;
@@ -1207,6 +1275,9 @@ void amuse_destroy(amuse_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   drop_schedules(ctx);
+  for (auto& g : ctx->dec_graphs) cudaGraphExecDestroy(g.exec);
+  ctx->dec_graphs.clear();
+  if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
   DevBuf* bufs[] = {&ctx->den.blob, &ctx->den.misc, &ctx->den.blob2, &ctx->den.vecs2, &ctx->dec.arena, &ctx->cond, &ctx->lat_tmp, &ctx->lat_out,
                     &ctx->one_coef, &ctx->dXA, &ctx->dXB, &ctx->dXC, &ctx->dQKV, &ctx->dO, &ctx->dH, &ctx->dSkip,
                     &ctx->dFeats, &ctx->dCvec, &ctx->dZero, &ctx->h2d, &ctx->tX[0], &ctx->tX[1], &ctx->tX[2],
