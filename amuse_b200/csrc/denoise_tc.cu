@@ -440,6 +440,17 @@ struct Chain {
       }
   }
 
+  // Waiting for an mbarrier: ONE warp per group polls it, the group's other three warps block on the group's named
+  // barrier (a hardware wait that issues nothing).  Probing warps execute instructions: with all 8 epilogue warps
+  // polling, the probes were 17% of everything the SM issued (profiles/r02_denoise_tc_lines.txt, first capture).
+#ifndef AMUSE_DN2_ALL_POLL
+  __device__ __forceinline__ void wait_group(uint64_t* bar, uint32_t parity) const {
+    if (q == 0) wait_bar(k, bar, parity);
+    bar_group();
+  }
+#else
+  __device__ __forceinline__ void wait_group(uint64_t* bar, uint32_t parity) const { wait_bar(k, bar, parity); }
+#endif
   // "my part of the B operand is written, and I am done with the accumulators": one arrive per warp
   __device__ __forceinline__ void signal_b() const {
     fence_proxy_async();   // my B-operand stores -> async proxy
@@ -450,7 +461,7 @@ struct Chain {
   // N-split stage: accumulator i (the tile of weight rank 2 rank + i) as soon as ITS MMAs have committed, my group's rows;
   // the epilogue of tile 0 runs under the MMAs of tile 1
   __device__ __forceinline__ void acc_nsplit(int i, float (&y)[kNR]) {
-    wait_bar(k, k.dbar(i), i ? dph1 : dph0);
+    wait_group(k.dbar(i), i ? dph1 : dph0);
     if (i) dph1 ^= 1;
     else dph0 ^= 1;
     tc_fence_after();
@@ -463,7 +474,7 @@ struct Chain {
   __device__ __forceinline__ void gemm_ksplit(float (&y)[kNR]) {
     stamp(0);
     signal_b();
-    wait_bar(k, k.dbar(0), dph0);
+    wait_group(k.dbar(0), dph0);
     stamp(1);
     dph0 ^= 1;
     ++g_tile;
@@ -490,7 +501,7 @@ struct Chain {
     }
   }
   __device__ __forceinline__ void xchg_recv(float (&v)[kNR]) {
-    wait_bar(k, k.xbar(xe & 1), (xe >> 1) & 1);
+    wait_group(k.xbar(xe & 1), (xe >> 1) & 1);
     const uint8_t* ps = smem + oPs + (xe & 1) * kPsSlot;
     const float2 a = *reinterpret_cast<const float2*>(ps + t * 1024 + f * 8);
     v[0] += a.x;

@@ -45,7 +45,7 @@ AUDIO_SAMPLES = 160000                     # 10 s at 16 kHz
 # dram__bytes_read.sum + dram__bytes_write.sum of one denoise_tc_kernel launch (ncu --set full,
 # profiles/r02_denoise_tc_full.txt): the 7.6 MB of fp16 hi/lo' weight planes are read from HBM once per launch and
 # served from L2 for every later step; activations never leave shared / tensor memory.
-DENOISE_LOOP_DRAM_BYTES = 7932416
+DENOISE_LOOP_DRAM_BYTES = 8057600
 METRIC = "SMPL-X pose frames/sec over full DDPM sampling (10 s clip, batch 64)"
 
 
