@@ -6,8 +6,10 @@ models/diffusion/viz/visualizer.py:344-364 and :192-225).  The caller (trainer.p
 v1 (``infer_gesture`` and the demo edit):  drop trans, freeze the 8 lower-body joints to frame 0, zero trans.
 v2 (dataset edits): zero the jaw joint 22; keep trans unless ``zero_trans`` / ``half_body``; the lower body
    is frozen only for ``half_body`` or ``zero_trans and freeze_init_LoBody``.
-Keys / dtypes follow the shipped fixtures (viz_dump/test/**/*_motion_smplx.npz): poses f32 [T,55,3],
-trans f64 [T,3], gender str, betas f64 [300], mocap_frame_rate f64 scalar.
+Keys / dtypes follow the reference's writers: v1 (the shipped fixtures viz_dump/test/**/*_motion_smplx.npz) poses f32
+[T,55,3], trans f64 [T,3]; v2 poses f64 (its jaw-zeroing ``np.concatenate`` with ``np.zeros`` promotes them,
+visualizer.py:197) and trans f32 when it is kept, f64 when it is zeroed; gender str, betas f64 [300],
+mocap_frame_rate f64 scalar.
 """
 from __future__ import annotations
 
@@ -42,7 +44,7 @@ def prepare_v2(feat: np.ndarray, zero_trans=False, freeze_init_lobody=False, hal
     f = np.array(feat, dtype=np.float32, copy=True).reshape(feat.shape[0], -1, 3)
     if f.shape[1] != 56:
         raise AssertionError(f"SMPL-X data should have 56 joints, got {f.shape[1]}.")
-    poses, trans = f[:, :-1, :].copy(), f[:, -1, :].astype(np.float64)
+    poses, trans = f[:, :-1, :].astype(np.float64), f[:, -1, :].copy()     # dtypes as the reference produces them (see header)
     poses[:, JAW_JOINT, :] = 0.0
     if zero_trans:
         trans = np.zeros((poses.shape[0], 3))
@@ -60,7 +62,7 @@ def write_motion_npz(path: Union[str, Path], poses: np.ndarray, trans: np.ndarra
     path = Path(path)
     path.parent.mkdir(parents=True, exist_ok=True)
     b = np.zeros(300, dtype=np.float64) if betas is None else np.asarray(betas, dtype=np.float64)
-    np.savez(path, poses=np.asarray(poses, dtype=np.float32), trans=np.asarray(trans, dtype=np.float64),
+    np.savez(path, poses=np.asarray(poses), trans=np.asarray(trans),
              gender=np.array(gender), betas=b, mocap_frame_rate=np.array(fps, dtype="float64"))
     return path if path.suffix == ".npz" else path.with_suffix(path.suffix + ".npz")
 

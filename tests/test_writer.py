@@ -46,6 +46,11 @@ def test_v2_variants():
     f = _feats(1)[0].numpy()
     poses, trans = writer.prepare_v2(f)
     assert np.abs(poses[:, writer.JAW_JOINT]).max() == 0 and np.allclose(trans, f.reshape(300, 56, 3)[:, -1])
+    # dtypes as the reference's v2 writer produces them (visualizer.py:192-222): the jaw-zeroing concatenate with np.zeros
+    # promotes poses to float64; a kept trans is the float32 slice, a zeroed one is np.zeros (float64)
+    assert poses.dtype == np.float64 and trans.dtype == np.float32
+    assert writer.prepare_v2(f, zero_trans=True)[1].dtype == np.float64
+    assert writer.prepare_v1(f)[0].dtype == np.float32 and writer.prepare_v1(f)[1].dtype == np.float64
     poses, trans = writer.prepare_v2(f, zero_trans=True, freeze_init_lobody=True)
     assert np.abs(trans).max() == 0 and np.abs(poses[:, 1] - poses[0, 1]).max() == 0
     poses, trans = writer.prepare_v2(f, zero_trans=True)
