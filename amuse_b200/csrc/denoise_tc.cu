@@ -231,19 +231,7 @@ __device__ __forceinline__ void produce_tile(const Ctx& k, const uint4* src, int
   constexpr int S = 2 * QUADS * 128 * 16;   // bytes between two of my units
   const uint4* s = src + (grp * QUADS + q) * 128;
   uint4 a[4] = {}, b[4] = {}, c[4] = {}, d[4] = {};
-  if (dbg & 16) {   // timing experiment: the same bytes as LDS.128 from (dummy) shared memory instead of LDG.128
-    const uint4* sm = reinterpret_cast<const uint4*>(k.smem + 61440) + (threadIdx.x & 255);   // 61440 + 48 KB < 120 KB
-#define DN2_LDS(R, J)            \
-  R[0] = sm[((J) & 1) * 1024];         \
-  R[1] = sm[((J) & 1) * 1024 + 256];   \
-  R[2] = sm[((J) & 1) * 1024 + 512];   \
-  R[3] = sm[((J) & 1) * 1024 + 768];
-    DN2_LDS(a, 0)
-    if constexpr (UNITS > 1) { DN2_LDS(b, 1) }
-    if constexpr (UNITS > 2) { DN2_LDS(c, 2) DN2_LDS(d, 3) }
-#undef DN2_LDS
-    asm volatile("" ::"r"(a[0].x), "r"(b[1].y), "r"(c[2].z), "r"(d[3].w));
-  } else if (!(dbg & 2)) {
+  if (!(dbg & 2)) {
 #define DN2_LOAD(R, J)                           \
   R[0] = ldg_stream<(J) * S>(s);                 \
   R[1] = ldg_stream<(J) * S + 512>(s);           \
