@@ -3,6 +3,7 @@
 #include "../../include/amuse_b200.h"
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cmath>
 #include <cstdarg>
@@ -157,6 +158,25 @@ struct amuse_ctx {
 };
 
 namespace {
+
+// NVTX ranges around the phases of the hot path (tracing hooks); AMUSE_NVTX=1 switches them on
+// (read once).  They show up in Nsight Systems / `ncu --nvtx` timelines: amuse.denoise, amuse.decode, amuse.ast, ...
+struct NvtxRange {
+  static bool enabled() {
+    static const bool on = [] {
+      const char* e = getenv("AMUSE_NVTX");
+      return e && e[0] == '1';
+    }();
+    return on;
+  }
+  bool active;
+  explicit NvtxRange(const char* name) : active(enabled()) {
+    if (active) nvtxRangePushA(name);
+  }
+  ~NvtxRange() {
+    if (active) nvtxRangePop();
+  }
+};
 
 int fail(amuse_ctx* c, int code, const char* fmt, ...) {
   char buf[512];
@@ -1327,6 +1347,7 @@ int amuse_load_weights(amuse_ctx* ctx, const char* name, const void* data, const
 }
 
 int amuse_finalize_weights(amuse_ctx* ctx, void* stream) {
+  NvtxRange nvtx_("amuse.finalize_weights");
   if (!ctx) return AMUSE_E_INVALID;
   cudaSetDevice(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1380,6 +1401,7 @@ int amuse_schedule(amuse_ctx* ctx, int n_steps, int sampler, float eta, int32_t*
 int amuse_denoise(amuse_ctx* ctx, int B, int n_steps, int sampler, float eta, int clip_sample, const float* latents0,
                   const float* z_con, const float* z_emo, const float* z_sty, const float* step_noise,
                   uint64_t seed, uint64_t clip_offset, float* latents_out, void* stream) {
+  NvtxRange nvtx_("amuse.denoise");
   if (int rc = check_ready(ctx, true, false)) return rc;
   if (B < 1 || !latents0 || !z_con || !latents_out) return fail(ctx, AMUSE_E_INVALID, "bad argument");
   cudaSetDevice(ctx->device);
@@ -1422,6 +1444,7 @@ int amuse_denoiser_eps(amuse_ctx* ctx, int B, int timestep, const float* sample,
 
 int amuse_decode(amuse_ctx* ctx, int B, const float* latents, float* feats6d, float* poses, float* trans,
                  void* stream) {
+  NvtxRange nvtx_("amuse.decode");
   if (int rc = check_ready(ctx, false, true)) return rc;
   if (B < 1 || !latents || (!feats6d && !poses)) return fail(ctx, AMUSE_E_INVALID, "bad argument");
   cudaSetDevice(ctx->device);
@@ -1429,6 +1452,7 @@ int amuse_decode(amuse_ctx* ctx, int B, const float* latents, float* feats6d, fl
 }
 
 int amuse_encode(amuse_ctx* ctx, int B, const float* feats, float* mu, float* logvar, void* stream) {
+  NvtxRange nvtx_("amuse.encode");
   if (!ctx) return AMUSE_E_INVALID;
   if (!ctx->enc.ready) return fail(ctx, AMUSE_E_STATE, "vae encoder weights not finalized");
   if (B < 1 || !feats || !mu || !logvar) return fail(ctx, AMUSE_E_INVALID, "bad argument");
@@ -1459,6 +1483,7 @@ int amuse_diffusion_backward(amuse_ctx* ctx, int B, int n_steps, int sampler, fl
                              const float* latents0, const float* z_con, const float* z_emo, const float* z_sty,
                              const float* step_noise, uint64_t seed, uint64_t clip_offset, float* latents_out,
                              float* feats6d, float* poses, float* trans, void* stream) {
+  NvtxRange nvtx_("amuse.diffusion_backward");
   if (int rc = check_ready(ctx, true, true)) return rc;
   if (!poses) return fail(ctx, AMUSE_E_INVALID, "poses must not be NULL");
   cudaSetDevice(ctx->device);
@@ -1477,6 +1502,7 @@ int amuse_diffusion_backward_host(amuse_ctx* ctx, int B, int n_steps, int sample
                                   const float* latents0, const float* z_con, const float* z_emo,
                                   const float* z_sty, const float* step_noise, uint64_t seed,
                                   uint64_t clip_offset, float* poses, float* trans, void* stream) {
+  NvtxRange nvtx_("amuse.diffusion_backward_host");
   if (int rc = check_ready(ctx, true, true)) return rc;
   if (B < 1 || !latents0 || !z_con || !poses) return fail(ctx, AMUSE_E_INVALID, "bad argument");
   cudaSetDevice(ctx->device);
@@ -1510,6 +1536,7 @@ int amuse_diffusion_backward_host(amuse_ctx* ctx, int B, int n_steps, int sample
 }
 
 int amuse_ast_features(amuse_ctx* ctx, int B, const float* fbank, float* con, float* emo, float* sty, void* stream) {
+  NvtxRange nvtx_("amuse.ast_features");
   if (!ctx || B < 1 || !fbank || !con || !emo || !sty) return fail(ctx, AMUSE_E_INVALID, "bad argument");
   if (!ast::ready(ctx->astw)) return fail(ctx, AMUSE_E_STATE, "ast weights not finalized");
   cudaSetDevice(ctx->device);
@@ -1564,6 +1591,7 @@ int amuse_debug_tc_gemm(amuse_ctx* ctx, int epi, int M, int N, int K, const floa
 
 int amuse_fbank(amuse_ctx* ctx, int B, int n_samples, const float* wave, float norm_mean, float norm_std,
                 float* fbank, void* stream) {
+  NvtxRange nvtx_("amuse.fbank");
   if (!ctx || B < 1 || !wave || !fbank) return fail(ctx, AMUSE_E_INVALID, "bad argument");
   if (n_samples < 400) return fail(ctx, AMUSE_E_INVALID, "need at least one 25 ms frame (400 samples)");
   cudaSetDevice(ctx->device);
