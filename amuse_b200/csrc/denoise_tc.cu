@@ -695,6 +695,7 @@ __device__ void Chain::run() {
     x[2] = t ? 0.f : ct[0];
     write_b(oBx, f, row0, x, nr);
     DN2_PROF(1);
+    float zn = noise;   // this step's noise draw (in-kernel Philox: evaluated under the first MMA phase, see the QKV stage)
 
     for (int layer = 0; layer < kLayers; ++layer) {
       // =============== output blocks: x = Linear(256->128)(cat(x, xs.pop())), K-split: CTA 0 holds x, CTA 1 the skip
@@ -720,6 +721,8 @@ __device__ void Chain::run() {
         const float sc = (q == 0) ? 0.17677669529663687f : 1.0f;
         float* const Q0 = reinterpret_cast<float*>(smem + oQKV) + row0 * kQkvLd + f;
         signal_b();
+        // the noise draw does not depend on the chain: off the critical path, while the first MMAs of the step run
+        if (layer == 0 && t == 0 && use_rng && coef[4] != 0.f) zn = philox_normal(p.seed, elem, static_cast<uint32_t>(step));
 #pragma unroll
         for (int i = 0; i < kVirt; ++i) {
           acc_nsplit(i, y);
@@ -821,10 +824,7 @@ __device__ void Chain::run() {
       float x0 = __fdiv_rn(__fsub_rn(z, __fmul_rn(coef[1], e)), coef[0]);
       if (p.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
       float out = __fadd_rn(__fmul_rn(coef[2], x0), __fmul_rn(coef[3], p.dir_uses_eps ? e : z));
-      if (coef[4] != 0.f) {
-        const float zn = use_rng ? philox_normal(p.seed, elem, static_cast<uint32_t>(step)) : noise;
-        out = __fadd_rn(out, __fmul_rn(coef[4], zn));
-      }
+      if (coef[4] != 0.f) out = __fadd_rn(out, __fmul_rn(coef[4], zn));
       z = out;
     }
     DN2_PROF(2 + kLayers * 10);

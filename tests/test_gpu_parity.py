@@ -364,26 +364,37 @@ def test_empty_batch(engine):
     assert engine.launch_count() == n0
 
 
-def test_wide_rows_layout_matches(engine, synthetic_weights, monkeypatch):
-    """The WIDE layout of the 2-clip kernel (AMUSE_WIDE_ROWS=1, a tuning hook read in amuse_create: 10-row GEMM
-    warps over 1/8 of K, partials parked in the idle exchange buffer) computes the same sampler as the default
-    layout: both against the oracle, on batch sizes with full and half-filled clusters and a 4-token ablation."""
+def test_ffma_fallback_kernels_match(engine, synthetic_weights, monkeypatch):
+    """The round-1 fp32 FFMA2 loop kernel (AMUSE_DENOISE_FFMA=1, the A/B switch next to the tcgen05 kernel) in its default
+    and WIDE layouts (AMUSE_WIDE_ROWS=1: 10-row GEMM warps over 1/8 of K, partials parked in the idle exchange buffer),
+    and the tcgen05 kernel, compute the same sampler: all three against the oracle, on batch sizes with full and
+    half-filled clusters, a 4-token ablation, and an ancestral run on the shared Philox stream."""
     from amuse_b200.engine import Engine
-    monkeypatch.setenv("AMUSE_WIDE_ROWS", "1")
-    wide = Engine("cuda:0")
-    monkeypatch.delenv("AMUSE_WIDE_ROWS")
+    engines = {}
+    for name, env in (("ffma", {"AMUSE_DENOISE_FFMA": "1"}), ("ffma-wide", {"AMUSE_DENOISE_FFMA": "1", "AMUSE_WIDE_ROWS": "1"})):
+        for k_, v_ in env.items():
+            monkeypatch.setenv(k_, v_)
+        engines[name] = Engine("cuda:0")
+        for k_ in env:
+            monkeypatch.delenv(k_)
+        engines[name].load_state_dict("denoiser", synthetic_weights["denoiser"])
+        engines[name].finalize()
     try:
-        wide.load_state_dict("denoiser", synthetic_weights["denoiser"])
-        wide.finalize()
         for B, sty in ((64, True), (35, False)):
             g = torch.Generator().manual_seed(77 + B)
             l0, con, emo = torch.randn(B, 128, generator=g), torch.randn(B, 256, generator=g), torch.randn(B, 256, generator=g)
             zs = torch.randn(B, 256, generator=g) if sty else None
             ref = R.sample_latents(synthetic_weights["denoiser"], l0, con, emo, zs, 10, "ddim")
-            a = wide.denoise(l0, con, emo, zs, n_steps=10, sampler="ddim").cpu()
-            b = engine.denoise(l0, con, emo, zs, n_steps=10, sampler="ddim").cpu()
-            ea, eb = (a - ref).abs().max().item(), (b - ref).abs().max().item()
-            print(f"[parity] wide-rows layout B={B}: wide max|d|={ea:.3e} default max|d|={eb:.3e}")
-            assert ea < 1e-4 and eb < 1e-4
+            errs = {"tcgen05": (engine.denoise(l0, con, emo, zs, n_steps=10, sampler="ddim").cpu() - ref).abs().max().item()}
+            for name, e in engines.items():
+                errs[name] = (e.denoise(l0, con, emo, zs, n_steps=10, sampler="ddim").cpu() - ref).abs().max().item()
+            print(f"[parity] loop kernels B={B}: " + "  ".join(f"{k_} max|d|={v_:.3e}" for k_, v_ in errs.items()))
+            assert all(v_ < 1e-4 for v_ in errs.values())
+        # the same stateless Philox draws in both kernel families: an ancestral run agrees to fp32 reordering
+        l0, con = torch.randn(5, 128, generator=g), torch.randn(5, 256, generator=g)
+        a = engine.denoise(l0, con, None, None, n_steps=20, sampler="ddpm", seed=9).cpu()
+        b = engines["ffma"].denoise(l0, con, None, None, n_steps=20, sampler="ddpm", seed=9).cpu()
+        assert (a - b).abs().max().item() < 2e-4 * max(1.0, a.abs().max().item())
     finally:
-        wide.close()
+        for e in engines.values():
+            e.close()
