@@ -142,6 +142,7 @@ struct amuse_ctx {
   };
   std::vector<DecGraph> dec_graphs;
   cudaStream_t cap_stream = nullptr;
+  bool attn_ffma = false;        // MotionPrior self-attention on the fp32 kernel (decode_kernels.cu) instead of attn_tc.cu
   bool den_ffma = false;         // denoise loop on the fp32 FFMA2 kernel (denoise_loop.cu) instead of the tcgen05 one
                                  // (denoise_tc.cu): AMUSE_DENOISE_FFMA=1, A/B switch for measurements
   DevBuf h2d;   // staging for the *_host entry point
@@ -1018,7 +1019,8 @@ int run_decode_tc_body(amuse_ctx* ctx, int B, const float* latents, float* feats
       g.M = M; g.N = 384; g.K = 128; g.bias = W + L.bqkv;
       g.C = qkv_ws; g.ldc = 384; g.q_cols = 128; g.q_scale = 0.17677669529663687f;
       CU(tc::gemm(tc::EPI_QKV, g, st));
-      CU(launch_self_attention_planes(qkv_ws, O.hi, O.lo, nb, kFrames, st));
+      if (ctx->attn_ffma) CU(launch_self_attention_planes(qkv_ws, O.hi, O.lo, nb, kFrames, st));
+      else CU(launch_self_attention_tc(qkv_ws, O.hi, O.lo, nb, kFrames, st));
       // y = norm2(norm1(x + out_proj(o)) + cross_vector)
       g = tc::GemmDesc{};
       g.A_hi = O.hi; g.A_lo = O.lo; g.lda = 128;
@@ -1202,7 +1204,8 @@ int run_encode_tc(amuse_ctx* ctx, int B, const float* feats, float* mu, float* l
       g.M = M; g.N = 384; g.K = 128; g.bias = W + L.bqkv;
       g.C = ctx->dQKV.p; g.ldc = 384; g.q_cols = 128; g.q_scale = 0.17677669529663687f;
       CU(tc::gemm(tc::EPI_QKV, g, st));
-      CU(launch_self_attention_planes(ctx->dQKV.p, O.hi, O.lo, nb, T, st));
+      if (ctx->attn_ffma) CU(launch_self_attention_planes(ctx->dQKV.p, O.hi, O.lo, nb, T, st));
+      else CU(launch_self_attention_tc(ctx->dQKV.p, O.hi, O.lo, nb, T, st));
       // y = norm1(x + out_proj(o))
       g = tc::GemmDesc{};
       g.A_hi = O.hi; g.A_lo = O.lo; g.lda = 128;
@@ -1280,6 +1283,7 @@ int amuse_create(amuse_ctx** out, int device_ordinal) {
   if (const char* e = getenv("AMUSE_DECODE_FFMA")) c->dec_use_tc = !(e[0] == '1');   // A/B switch for measurements
   if (const char* e = getenv("AMUSE_PRUNE_LAST")) c->prune_last = (e[0] != '0');
   if (const char* e = getenv("AMUSE_DENOISE_FFMA")) c->den_ffma = (e[0] == '1');
+  if (const char* e = getenv("AMUSE_ATTN_FFMA")) c->attn_ffma = (e[0] == '1');
   if (const char* e = getenv("AMUSE_DECODE_GRAPH")) c->dec_graph = (e[0] != '0');
   if (const char* e = getenv("AMUSE_WIDE_ROWS")) c->wide_rows = (e[0] != '0');
   if (cudaMalloc(&c->d_prof, 512 * sizeof(long long)) != cudaSuccess) {

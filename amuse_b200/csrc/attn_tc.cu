@@ -1,0 +1,314 @@
+// Self-attention of MotionPrior's transformer layers on tcgen05 (reference cross_attention.py:323-345, nn.MultiheadAttention
+// with 4 heads of 32 over the 300 decoder frames / 302 encoder tokens): softmax(q k^T) v for one (clip, head) per CTA.
+//
+//   * fp32-class accuracy from fp16 operands: x = hi + lo with hi = fp16(x), lo = fp16(x - hi) (values here are O(1); the
+//     low plane's absolute error is <= 2^-25).  A shared-memory operand row holds [hi(32) | lo(32)] = one 128-byte
+//     SWIZZLE_128B row, so  S = Q_hi K_hi^T + Q_hi K_lo^T + Q_lo K_hi^T  is six K = 16 MMAs per key chunk that differ only in
+//     the 32-byte k-step offsets of their descriptors, all into one fp32 accumulator (queries on the 128 TMEM lanes, keys
+//     on the columns).
+//   * softmax in the accumulator's own layout: thread = query row, two warps per lane quadrant split the keys at column
+//     160; row max, exp2, row sum are in-thread.  P goes back to TMEM as the A operand of the second GEMM (fp16 pairs
+//     per 32-bit column): P_hi in place over the consumed score columns of the same warp, P_lo in the free columns.
+//   * O = P_hi V_hi + P_hi V_lo + P_lo V_hi: A from TMEM, B = V^T (keys contiguous) written transposed into shared
+//     memory when the head's K / V are converted, once per CTA; 3 query tiles of 128 reuse them.
+//   * the result leaves as TF32 hi / lo planes, the A operand of the out_proj GEMM (tc_gemm.cu).
+// TMEM columns: S [0, 320) | O [320, 352) | P_lo [352, 512).
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "decode_kernels.cuh"
+#include "tc_ptx.cuh"
+
+namespace amuse {
+namespace dec {
+
+namespace {
+
+using namespace tcp;
+
+constexpr int kMaxKeys = 320;
+constexpr int kSplit = 160;           // keys [0, 160) -> warps 0..3, [160, 320) -> warps 4..7
+constexpr int kAttnThreads = 256;
+constexpr int oK = 0;                           // [320 keys][hi 32 | lo 32] fp16
+constexpr int oQ = oK + kMaxKeys * 128;         // [128 queries][hi 32 | lo 32]
+constexpr int oVh = oQ + 128 * 128;             // V^T hi: [5 boxes of 64 keys][32 dims][128 B]
+constexpr int oVl = oVh + 5 * 4096;             // V^T lo
+constexpr int oRed = oVl + 5 * 4096;            // float smax[2][128] | ssum[2][128]
+constexpr int oBar = oRed + 2048;               // 2 mbarriers + the TMEM base slot
+constexpr int kAttnSmem = oBar + 64 + 1024;     // + slack for the 1024-byte alignment of the operand base
+static_assert(oQ % 1024 == 0 && oVh % 1024 == 0 && oVl % 1024 == 0, "operands must be 1024-B aligned");
+constexpr uint32_t cS = 0, cO = 320, cPl = 352;
+
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {   // D = F32, A = B = F16, both K-major
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+      "l"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
+      "r"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// 16 columns of my TMEM lane; the registers are defined only after the wait, so they pass through it
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// (a, b) -> fp16 pair of the high parts and of the remainders; element a in the low half (the lower k)
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void wait_bounded(uint64_t* bar, uint32_t parity) {
+  for (int i = 0; i < (1 << 24); ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();   // an MMA that never completes: fail loudly instead of hanging the device
+}
+
+// one row of a [rows][hi 32 | lo 32] operand: the float4 at dims [4 c4, 4 c4 + 4)
+__device__ __forceinline__ void store_row_chunk(uint8_t* base, int row, int c4, float4 v) {
+  uint2 hi, lo;
+  split_pair(v.x, v.y, hi.x, lo.x);
+  split_pair(v.z, v.w, hi.y, lo.y);
+  uint8_t* r = base + row * 128 + (c4 & 1) * 8;
+  const int sw = row & 7;
+  *reinterpret_cast<uint2*>(r + (((c4 >> 1) ^ sw) << 4)) = hi;
+  *reinterpret_cast<uint2*>(r + ((((c4 >> 1) + 4) ^ sw) << 4)) = lo;
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+self_attention_tc_kernel(const float* __restrict__ qkv, float* __restrict__ out_hi, float* __restrict__ out_lo, int frames) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* sbar = reinterpret_cast<uint64_t*>(smem + oBar);
+  uint64_t* obar = sbar + 1;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + oBar + 16);
+  float* smax = reinterpret_cast<float*>(smem + oRed);
+  float* ssum = smax + 256;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int nk = (frames + 15) & ~15;                    // keys rounded up to the MMA's k-step
+  const int n0 = nk < kSplit ? nk : kSplit, n1 = nk - n0;   // the two key chunks of the score GEMM
+  const float* base = qkv + static_cast<size_t>(b) * frames * 384 + h * 32;
+
+  if (warp == 0) tmem_alloc<512>(tslot);
+  if (tid == 0) {
+    mbar_init(sbar, 1);
+    mbar_init(obar, 1);
+    fence_mbar_init();
+  }
+  // ---- the head's keys and values -> fp16 hi | lo operands (rows / keys beyond `frames` are zero)
+  for (int idx = tid; idx < nk * 8; idx += kAttnThreads) {
+    const int j = idx >> 3, c4 = idx & 7;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < frames) v = *reinterpret_cast<const float4*>(base + static_cast<size_t>(j) * 384 + 128 + c4 * 4);
+    store_row_chunk(smem + oK, j, c4, v);
+  }
+  for (int idx = tid; idx < (nk >> 4) * 64; idx += kAttnThreads) {
+    // a warp covers 8 key pairs x 4 dim chunks: its 4-byte stores spread over 16 banks
+    const int j = (idx >> 6) * 16 + (idx & 7) * 2, c = ((idx >> 5) & 1) * 4 + ((idx >> 3) & 3);
+    float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+    if (j < frames) va = *reinterpret_cast<const float4*>(base + static_cast<size_t>(j) * 384 + 256 + c * 4);
+    if (j + 1 < frames) vb = *reinterpret_cast<const float4*>(base + static_cast<size_t>(j + 1) * 384 + 256 + c * 4);
+    const float a4[4] = {va.x, va.y, va.z, va.w}, b4[4] = {vb.x, vb.y, vb.z, vb.w};
+    const int kc = j & 63;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int d = c * 4 + i;
+      uint32_t hi, lo;
+      split_pair(a4[i], b4[i], hi, lo);
+      const int off = (j >> 6) * 4096 + d * 128 + (((kc >> 3) ^ (d & 7)) << 4) + (kc & 7) * 2;
+      *reinterpret_cast<uint32_t*>(smem + oVh + off) = hi;
+      *reinterpret_cast<uint32_t*>(smem + oVl + off) = lo;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+  const int q4 = warp & 3, hf = warp >> 2;
+  const uint32_t lane_taddr = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
+  const int row = q4 * 32 + lane;                 // my query row of the tile = my TMEM lane
+  const int col0 = hf * kSplit;                   // my first key
+  const int nchunk = (hf ? n1 : n0) >> 4;         // my 16-key chunks
+  const uint64_t dQ = umma_desc(smem_u32(smem + oQ)), dK0 = umma_desc(smem_u32(smem + oK)),
+                 dK1 = umma_desc(smem_u32(smem + oK + kSplit * 128)), dVh = umma_desc(smem_u32(smem + oVh)),
+                 dVl = umma_desc(smem_u32(smem + oVl));
+  const uint32_t id0 = idesc_f16(128, n0), id1 = idesc_f16(128, n1 ? n1 : 16), idO = idesc_f16(128, 32);
+  constexpr float kLog2e = 1.4426950408889634f;
+  uint32_t ph = 0;
+
+  for (int q0 = 0; q0 < frames; q0 += 128) {
+    // ---- this tile's queries -> A operand
+    for (int idx = tid; idx < 128 * 8; idx += kAttnThreads) {
+      const int r = idx >> 3, c4 = idx & 7;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q0 + r < frames) v = *reinterpret_cast<const float4*>(base + static_cast<size_t>(q0 + r) * 384 + c4 * 4);
+      store_row_chunk(smem + oQ, r, c4, v);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        // k-steps of an operand row: 0, 1 = hi, 2, 3 = lo (32 bytes each): hi.hi, hi.lo, lo.hi
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+          const int ja = (t < 4) ? (t & 1) : (t - 2), jb = (t < 2) ? t : (t < 4) ? t : (t - 4);
+          umma_f16_ss(tmem + cS, dQ + static_cast<uint64_t>(ja * 2), dK0 + static_cast<uint64_t>(jb * 2), id0, t ? 1u : 0u);
+        }
+        if (n1 > 0) {
+#pragma unroll
+          for (int t = 0; t < 6; ++t) {
+            const int ja = (t < 4) ? (t & 1) : (t - 2), jb = (t < 2) ? t : (t < 4) ? t : (t - 4);
+            umma_f16_ss(tmem + cS + kSplit, dQ + static_cast<uint64_t>(ja * 2), dK1 + static_cast<uint64_t>(jb * 2), id1,
+                        t ? 1u : 0u);
+          }
+        }
+        umma_commit(sbar);
+      }
+      __syncwarp();
+    }
+    wait_bounded(sbar, ph);
+    tc_fence_after();
+
+    // ---- pass 1: row max over my keys
+    float m = -INFINITY;
+    for (int c = 0; c < nchunk; ++c) {
+      float s[16];
+      tmem_ld16(lane_taddr + cS + col0 + 16 * c, s);
+      const int k0 = col0 + 16 * c;
+      if (k0 + 16 <= frames) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) m = fmaxf(m, s[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (k0 + i < frames) m = fmaxf(m, s[i]);
+      }
+    }
+    smax[hf * 128 + row] = m;
+    __syncthreads();
+    m = fmaxf(smax[row], smax[128 + row]);
+    const float mneg = -m * kLog2e;
+
+    // ---- pass 2: p = exp(s - max), row sum, P -> TMEM as fp16 hi / lo pairs
+    float l = 0.f;
+    for (int c = 0; c < nchunk; ++c) {
+      float s[16];
+      tmem_ld16(lane_taddr + cS + col0 + 16 * c, s);
+      const int k0 = col0 + 16 * c;
+      uint32_t phi[8], plo[8];
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) {
+        float pa = ex2(fmaf(s[i], kLog2e, mneg)), pb = ex2(fmaf(s[i + 1], kLog2e, mneg));
+        if (k0 + i >= frames) pa = 0.f;
+        if (k0 + i + 1 >= frames) pb = 0.f;
+        l += pa + pb;
+        split_pair(pa, pb, phi[i >> 1], plo[i >> 1]);
+      }
+      tmem_st8(lane_taddr + cS + col0 + 8 * c, phi);               // in place: columns this warp has already consumed
+      tmem_st8(lane_taddr + cPl + ((col0 + 16 * c) >> 1), plo);
+    }
+    ssum[hf * 128 + row] = l;
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        const int ksteps = nk >> 4;
+        for (int kk = 0; kk < ksteps; ++kk) {
+          const uint32_t ahi = tmem + cS + (kk < 10 ? 8 * kk : kSplit + 8 * (kk - 10)), alo = tmem + cPl + 8 * kk;
+          const uint64_t off = static_cast<uint64_t>(((kk >> 2) * 4096 + (kk & 3) * 32) >> 4);
+          umma_f16_ts(tmem + cO, ahi, dVh + off, idO, kk ? 1u : 0u);
+          umma_f16_ts(tmem + cO, ahi, dVl + off, idO, 1u);
+          umma_f16_ts(tmem + cO, alo, dVh + off, idO, 1u);
+        }
+        umma_commit(obar);
+      }
+      __syncwarp();
+    }
+    wait_bounded(obar, ph);
+    tc_fence_after();
+    ph ^= 1;
+
+    // ---- O / row sum -> TF32 hi / lo planes; warp half hf writes dims [16 hf, 16 hf + 16) of its rows
+    {
+      float o[16];
+      tmem_ld16(lane_taddr + cO + 16 * hf, o);
+      const float inv = 1.0f / (ssum[row] + ssum[128 + row]);
+      if (q0 + row < frames) {
+        const size_t off = (static_cast<size_t>(b) * frames + q0 + row) * 128 + h * 32 + 16 * hf;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float4 hi, lo;
+          split_tf32(o[4 * c + 0] * inv, hi.x, lo.x);
+          split_tf32(o[4 * c + 1] * inv, hi.y, lo.y);
+          split_tf32(o[4 * c + 2] * inv, hi.z, lo.z);
+          split_tf32(o[4 * c + 3] * inv, hi.w, lo.w);
+          *reinterpret_cast<float4*>(out_hi + off + 4 * c) = hi;
+          *reinterpret_cast<float4*>(out_lo + off + 4 * c) = lo;
+        }
+      }
+    }
+    tc_fence_before();   // my reads of O and of the score columns precede the next tile's MMAs (ordered by its __syncthreads)
+  }
+
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_self_attention_tc(const float* qkv, float* out_hi, float* out_lo, int clips, int frames,
+                                     cudaStream_t st) {
+  if (frames < 1 || frames > kMaxKeys) return cudaErrorInvalidValue;
+  static PerDeviceOnce once;
+  if (cudaError_t e = once.run([] {
+        return cudaFuncSetAttribute(self_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+      }))
+    return e;
+  self_attention_tc_kernel<<<dim3(kHeads, clips), kAttnThreads, kAttnSmem, st>>>(qkv, out_hi, out_lo, frames);
+  return cudaGetLastError();
+}
+
+}  // namespace dec
+}  // namespace amuse

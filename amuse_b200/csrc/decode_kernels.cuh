@@ -37,6 +37,11 @@ cudaError_t launch_self_attention(const float* qkv /*[M][384]*/, float* out /*[M
 cudaError_t launch_self_attention_planes(const float* qkv, float* out_hi, float* out_lo, int clips, int frames,
                                          cudaStream_t st);
 
+// the same on tcgen05 (attn_tc.cu; frames <= 320): one CTA per (clip, head), fp16 hi/lo operands, fp32-class accuracy.
+// The default of the tensor-core decode / encode path; AMUSE_ATTN_FFMA=1 (read at amuse_create) keeps the fp32 kernel.
+cudaError_t launch_self_attention_tc(const float* qkv, float* out_hi, float* out_lo, int clips, int frames,
+                                     cudaStream_t st);
+
 // cvec[l][b] = out_proj_l(W_v,l z_b + b_v,l) + b_o,l for the 9 decoder layers (1-key cross attention).
 cudaError_t launch_cross_vectors(const float* z /*[B][128]*/, const float* wv_t /*[9][128][128]*/,
                                  const float* bv /*[9][128]*/, const float* wo_t /*[9][128][128]*/,

@@ -398,3 +398,34 @@ def test_ffma_fallback_kernels_match(engine, synthetic_weights, monkeypatch):
     finally:
         for e in engines.values():
             e.close()
+
+
+def test_attention_kernels_match(engine, synthetic_weights, monkeypatch):
+    """MotionPrior's self-attention: the tcgen05 kernel (attn_tc.cu, the default) and the fp32 CUDA-core kernel
+    (AMUSE_ATTN_FFMA=1) against the oracle's decode and encode -- 300 decoder frames (3 query tiles, the last with 44
+    rows; keys padded 300 -> 304) and 302 encoder tokens."""
+    from amuse_b200.engine import Engine
+    from oracle.make_golden import synthetic_motion
+    monkeypatch.setenv("AMUSE_ATTN_FFMA", "1")
+    ffma = Engine("cuda:0")
+    monkeypatch.delenv("AMUSE_ATTN_FFMA")
+    ffma.load_state_dict("vae", synthetic_weights["vae"])
+    ffma.finalize()
+    try:
+        z = torch.randn(3, 128, generator=torch.Generator().manual_seed(11))
+        ref = R.vae_decode(synthetic_weights["vae"], z)
+        errs = {}
+        for name, e in (("tcgen05", engine), ("ffma", ffma)):
+            _, _, feats = e.decode(z, want_feats=True)
+            errs[name] = (feats.cpu() - ref).abs().max().item()
+        print("[parity] decode, attention kernels: " + "  ".join(f"{k_} max|d|={v_:.3e}" for k_, v_ in errs.items()))
+        assert all(v_ < TOL_FEATS for v_ in errs.values())
+        poses, trans = synthetic_motion(2)
+        feats = engine.motion_to_feats(poses, trans)
+        mu_a, lv_a = engine.encode(feats)
+        mu_b, lv_b = ffma.encode(feats)
+        d = max((mu_a - mu_b).abs().max().item(), (lv_a - lv_b).abs().max().item())
+        print(f"[parity] encode, attention kernels: max|d mu, logvar| = {d:.3e}")
+        assert d < 2 * TOL_FEATS
+    finally:
+        ffma.close()
