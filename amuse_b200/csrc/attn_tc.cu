@@ -6,9 +6,9 @@
 //     SWIZZLE_128B row, so  S = Q_hi K_hi^T + Q_hi K_lo^T + Q_lo K_hi^T  is six K = 16 MMAs per key chunk that differ only in
 //     the 32-byte k-step offsets of their descriptors, all into one fp32 accumulator (queries on the 128 TMEM lanes, keys
 //     on the columns).
-//   * softmax in the accumulator's own layout: thread = query row, two warps per lane quadrant split the keys at column
-//     160; row max, exp2, row sum are in-thread.  P goes back to TMEM as the A operand of the second GEMM (fp16 pairs
-//     per 32-bit column): P_hi in place over the consumed score columns of the same warp, P_lo in the free columns.
+//   * softmax in the accumulator's own layout: thread = query row, four warps per lane quadrant take 80 keys each; row
+//     max, exp2, row sum are in-thread.  P goes back to TMEM as the A operand of the second GEMM (fp16 pairs per 32-bit
+//     column): P_hi in place over the consumed score columns of the same warp, P_lo in the free columns.
 //   * O = P_hi V_hi + P_hi V_lo + P_lo V_hi: A from TMEM, B = V^T (keys contiguous) written transposed into shared
 //     memory when the head's K / V are converted, once per CTA; 3 query tiles of 128 reuse them.
 //   * the result leaves as TF32 hi / lo planes, the A operand of the out_proj GEMM (tc_gemm.cu).
@@ -27,14 +27,15 @@ namespace {
 using namespace tcp;
 
 constexpr int kMaxKeys = 320;
-constexpr int kSplit = 160;           // keys [0, 160) -> warps 0..3, [160, 320) -> warps 4..7
-constexpr int kAttnThreads = 256;
+constexpr int kSplit = 160;           // the score GEMM runs as two MMAs chunks: keys [0, 160) and [160, 320)
+constexpr int kPart = 80;             // softmax: 4 warps per TMEM lane quadrant, 80 keys (5 chunks of 16) each
+constexpr int kAttnThreads = 512;     // 16 warps: the softmax is a chain of TMEM loads per warp, 4 warps per scheduler hide it
 constexpr int oK = 0;                           // [320 keys][hi 32 | lo 32] fp16
 constexpr int oQ = oK + kMaxKeys * 128;         // [128 queries][hi 32 | lo 32]
 constexpr int oVh = oQ + 128 * 128;             // V^T hi: [5 boxes of 64 keys][32 dims][128 B]
 constexpr int oVl = oVh + 5 * 4096;             // V^T lo
-constexpr int oRed = oVl + 5 * 4096;            // float smax[2][128] | ssum[2][128]
-constexpr int oBar = oRed + 2048;               // 2 mbarriers + the TMEM base slot
+constexpr int oRed = oVl + 5 * 4096;            // float smax[4][128] | ssum[4][128]
+constexpr int oBar = oRed + 4096;               // 2 mbarriers + the TMEM base slot
 constexpr int kAttnSmem = oBar + 64 + 1024;     // + slack for the 1024-byte alignment of the operand base
 static_assert(oQ % 1024 == 0 && oVh % 1024 == 0 && oVl % 1024 == 0, "operands must be 1024-B aligned");
 constexpr uint32_t cS = 0, cO = 320, cPl = 352;
@@ -72,6 +73,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
                : "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               :
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
@@ -116,7 +130,7 @@ self_attention_tc_kernel(const float* __restrict__ qkv, float* __restrict__ out_
   uint64_t* obar = sbar + 1;
   uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + oBar + 16);
   float* smax = reinterpret_cast<float*>(smem + oRed);
-  float* ssum = smax + 256;
+  float* ssum = smax + 512;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x, b = blockIdx.y;
@@ -130,40 +144,62 @@ self_attention_tc_kernel(const float* __restrict__ qkv, float* __restrict__ out_
     mbar_init(obar, 1);
     fence_mbar_init();
   }
-  // ---- the head's keys and values -> fp16 hi | lo operands (rows / keys beyond `frames` are zero)
-  for (int idx = tid; idx < nk * 8; idx += kAttnThreads) {
-    const int j = idx >> 3, c4 = idx & 7;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (j < frames) v = *reinterpret_cast<const float4*>(base + static_cast<size_t>(j) * 384 + 128 + c4 * 4);
-    store_row_chunk(smem + oK, j, c4, v);
-  }
-  for (int idx = tid; idx < (nk >> 4) * 64; idx += kAttnThreads) {
-    // a warp covers 8 key pairs x 4 dim chunks: its 4-byte stores spread over 16 banks
-    const int j = (idx >> 6) * 16 + (idx & 7) * 2, c = ((idx >> 5) & 1) * 4 + ((idx >> 3) & 3);
-    float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
-    if (j < frames) va = *reinterpret_cast<const float4*>(base + static_cast<size_t>(j) * 384 + 256 + c * 4);
-    if (j + 1 < frames) vb = *reinterpret_cast<const float4*>(base + static_cast<size_t>(j + 1) * 384 + 256 + c * 4);
-    const float a4[4] = {va.x, va.y, va.z, va.w}, b4[4] = {vb.x, vb.y, vb.z, vb.w};
-    const int kc = j & 63;
+  // ---- the head's keys and values -> fp16 hi | lo operands (rows / keys beyond `frames` are zero).  All global loads of
+  // a phase are issued before the first conversion: the latency of L2 is paid once, not once per item.
+  {
+    constexpr int kIt = kMaxKeys * 8 / kAttnThreads;
+    float4 v[kIt];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int d = c * 4 + i;
-      uint32_t hi, lo;
-      split_pair(a4[i], b4[i], hi, lo);
-      const int off = (j >> 6) * 4096 + d * 128 + (((kc >> 3) ^ (d & 7)) << 4) + (kc & 7) * 2;
-      *reinterpret_cast<uint32_t*>(smem + oVh + off) = hi;
-      *reinterpret_cast<uint32_t*>(smem + oVl + off) = lo;
+    for (int it = 0; it < kIt; ++it) {
+      const int idx = tid + it * kAttnThreads, j = idx >> 3, c4 = idx & 7;
+      v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < frames) v[it] = *reinterpret_cast<const float4*>(base + static_cast<size_t>(j) * 384 + 128 + c4 * 4);
+    }
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+      const int idx = tid + it * kAttnThreads;
+      if (idx < nk * 8) store_row_chunk(smem + oK, idx >> 3, idx & 7, v[it]);
+    }
+  }
+  {
+    constexpr int kIt = (kMaxKeys / 16 * 64 + kAttnThreads - 1) / kAttnThreads;
+    float4 va[kIt], vb[kIt];
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+      // a warp covers 8 key pairs x 4 dim chunks: its 4-byte stores spread over 16 banks
+      const int idx = tid + it * kAttnThreads;
+      const int j = (idx >> 6) * 16 + (idx & 7) * 2, c = ((idx >> 5) & 1) * 4 + ((idx >> 3) & 3);
+      va[it] = vb[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < frames) va[it] = *reinterpret_cast<const float4*>(base + static_cast<size_t>(j) * 384 + 256 + c * 4);
+      if (j + 1 < frames) vb[it] = *reinterpret_cast<const float4*>(base + static_cast<size_t>(j + 1) * 384 + 256 + c * 4);
+    }
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+      const int idx = tid + it * kAttnThreads;
+      if (idx >= (nk >> 4) * 64) continue;
+      const int j = (idx >> 6) * 16 + (idx & 7) * 2, c = ((idx >> 5) & 1) * 4 + ((idx >> 3) & 3);
+      const float a4[4] = {va[it].x, va[it].y, va[it].z, va[it].w}, b4[4] = {vb[it].x, vb[it].y, vb[it].z, vb[it].w};
+      const int kc = j & 63;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int d = c * 4 + i;
+        uint32_t hi, lo;
+        split_pair(a4[i], b4[i], hi, lo);
+        const int off = (j >> 6) * 4096 + d * 128 + (((kc >> 3) ^ (d & 7)) << 4) + (kc & 7) * 2;
+        *reinterpret_cast<uint32_t*>(smem + oVh + off) = hi;
+        *reinterpret_cast<uint32_t*>(smem + oVl + off) = lo;
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tslot;
-  const int q4 = warp & 3, hf = warp >> 2;
+  const int q4 = warp & 3, part = warp >> 2;
   const uint32_t lane_taddr = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
   const int row = q4 * 32 + lane;                 // my query row of the tile = my TMEM lane
-  const int col0 = hf * kSplit;                   // my first key
-  const int nchunk = (hf ? n1 : n0) >> 4;         // my 16-key chunks
+  const int col0 = part * kPart;                  // my first key
+  const int nchunk = (nk - col0 < kPart ? (nk - col0 > 0 ? nk - col0 : 0) : kPart) >> 4;   // my 16-key chunks
   const uint64_t dQ = umma_desc(smem_u32(smem + oQ)), dK0 = umma_desc(smem_u32(smem + oK)),
                  dK1 = umma_desc(smem_u32(smem + oK + kSplit * 128)), dVh = umma_desc(smem_u32(smem + oVh)),
                  dVl = umma_desc(smem_u32(smem + oVl));
@@ -171,15 +207,29 @@ self_attention_tc_kernel(const float* __restrict__ qkv, float* __restrict__ out_
   constexpr float kLog2e = 1.4426950408889634f;
   uint32_t ph = 0;
 
-  for (int q0 = 0; q0 < frames; q0 += 128) {
-    // ---- this tile's queries -> A operand
-    for (int idx = tid; idx < 128 * 8; idx += kAttnThreads) {
-      const int r = idx >> 3, c4 = idx & 7;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (q0 + r < frames) v = *reinterpret_cast<const float4*>(base + static_cast<size_t>(q0 + r) * 384 + c4 * 4);
-      store_row_chunk(smem + oQ, r, c4, v);
+  // a tile's queries -> A operand: 2 row chunks per thread, loaded one tile ahead (under the score MMAs and pass 1)
+  constexpr int kQIt = 128 * 8 / kAttnThreads;
+  float4 qv[kQIt];
+  auto load_q = [&](int q0) {
+#pragma unroll
+    for (int it = 0; it < kQIt; ++it) {
+      const int idx = tid + it * kAttnThreads, r = idx >> 3, c4 = idx & 7;
+      qv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q0 + r < frames) qv[it] = *reinterpret_cast<const float4*>(base + static_cast<size_t>(q0 + r) * 384 + c4 * 4);
     }
-    fence_proxy_async();
+  };
+  auto store_q = [&]() {
+#pragma unroll
+    for (int it = 0; it < kQIt; ++it) {
+      const int idx = tid + it * kAttnThreads;
+      store_row_chunk(smem + oQ, idx >> 3, idx & 7, qv[it]);
+    }
+    fence_proxy_async();   // here, not at the loop top: behind the epilogue's global stores the fence waits for them to drain
+  };
+  load_q(0);
+  store_q();
+
+  for (int q0 = 0; q0 < frames; q0 += 128) {
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -203,6 +253,8 @@ self_attention_tc_kernel(const float* __restrict__ qkv, float* __restrict__ out_
       }
       __syncwarp();
     }
+    const bool more = q0 + 128 < frames;
+    if (more) load_q(q0 + 128);
     wait_bounded(sbar, ph);
     tc_fence_after();
 
@@ -221,9 +273,10 @@ self_attention_tc_kernel(const float* __restrict__ qkv, float* __restrict__ out_
           if (k0 + i < frames) m = fmaxf(m, s[i]);
       }
     }
-    smax[hf * 128 + row] = m;
+    smax[part * 128 + row] = m;
+    if (more) store_q();   // the score MMAs are done with the previous tile's queries
     __syncthreads();
-    m = fmaxf(smax[row], smax[128 + row]);
+    m = fmaxf(fmaxf(smax[row], smax[128 + row]), fmaxf(smax[256 + row], smax[384 + row]));
     const float mneg = -m * kLog2e;
 
     // ---- pass 2: p = exp(s - max), row sum, P -> TMEM as fp16 hi / lo pairs
@@ -233,18 +286,27 @@ self_attention_tc_kernel(const float* __restrict__ qkv, float* __restrict__ out_
       tmem_ld16(lane_taddr + cS + col0 + 16 * c, s);
       const int k0 = col0 + 16 * c;
       uint32_t phi[8], plo[8];
+      if (k0 + 16 <= frames) {
 #pragma unroll
-      for (int i = 0; i < 16; i += 2) {
-        float pa = ex2(fmaf(s[i], kLog2e, mneg)), pb = ex2(fmaf(s[i + 1], kLog2e, mneg));
-        if (k0 + i >= frames) pa = 0.f;
-        if (k0 + i + 1 >= frames) pb = 0.f;
-        l += pa + pb;
-        split_pair(pa, pb, phi[i >> 1], plo[i >> 1]);
+        for (int i = 0; i < 16; i += 2) {
+          const float pa = ex2(fmaf(s[i], kLog2e, mneg)), pb = ex2(fmaf(s[i + 1], kLog2e, mneg));
+          l += pa + pb;
+          split_pair(pa, pb, phi[i >> 1], plo[i >> 1]);
+        }
+      } else {   // the chunk that holds the padding keys
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          float pa = ex2(fmaf(s[i], kLog2e, mneg)), pb = ex2(fmaf(s[i + 1], kLog2e, mneg));
+          if (k0 + i >= frames) pa = 0.f;
+          if (k0 + i + 1 >= frames) pb = 0.f;
+          l += pa + pb;
+          split_pair(pa, pb, phi[i >> 1], plo[i >> 1]);
+        }
       }
       tmem_st8(lane_taddr + cS + col0 + 8 * c, phi);               // in place: columns this warp has already consumed
       tmem_st8(lane_taddr + cPl + ((col0 + 16 * c) >> 1), plo);
     }
-    ssum[hf * 128 + row] = l;
+    ssum[part * 128 + row] = l;
     tmem_st_wait();
     tc_fence_before();
     __syncthreads();
@@ -253,7 +315,7 @@ self_attention_tc_kernel(const float* __restrict__ qkv, float* __restrict__ out_
       if (elect_one()) {
         const int ksteps = nk >> 4;
         for (int kk = 0; kk < ksteps; ++kk) {
-          const uint32_t ahi = tmem + cS + (kk < 10 ? 8 * kk : kSplit + 8 * (kk - 10)), alo = tmem + cPl + 8 * kk;
+          const uint32_t ahi = tmem + cS + (kk / 5) * kPart + 8 * (kk % 5), alo = tmem + cPl + 8 * kk;   // P_hi sits where its warp consumed the scores
           const uint64_t off = static_cast<uint64_t>(((kk >> 2) * 4096 + (kk & 3) * 32) >> 4);
           umma_f16_ts(tmem + cO, ahi, dVh + off, idO, kk ? 1u : 0u);
           umma_f16_ts(tmem + cO, ahi, dVl + off, idO, 1u);
@@ -267,15 +329,15 @@ self_attention_tc_kernel(const float* __restrict__ qkv, float* __restrict__ out_
     tc_fence_after();
     ph ^= 1;
 
-    // ---- O / row sum -> TF32 hi / lo planes; warp half hf writes dims [16 hf, 16 hf + 16) of its rows
+    // ---- O / row sum -> TF32 hi / lo planes; warp `part` writes dims [8 part, 8 part + 8) of its rows
     {
-      float o[16];
-      tmem_ld16(lane_taddr + cO + 16 * hf, o);
-      const float inv = 1.0f / (ssum[row] + ssum[128 + row]);
+      float o[8];
+      tmem_ld8(lane_taddr + cO + 8 * part, o);
+      const float inv = 1.0f / ((ssum[row] + ssum[128 + row]) + (ssum[256 + row] + ssum[384 + row]));
       if (q0 + row < frames) {
-        const size_t off = (static_cast<size_t>(b) * frames + q0 + row) * 128 + h * 32 + 16 * hf;
+        const size_t off = (static_cast<size_t>(b) * frames + q0 + row) * 128 + h * 32 + 8 * part;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           float4 hi, lo;
           split_tf32(o[4 * c + 0] * inv, hi.x, lo.x);
           split_tf32(o[4 * c + 1] * inv, hi.y, lo.y);

@@ -9,9 +9,12 @@
 //               (operands straight from shared memory through UMMA descriptors), then
 //               tcgen05.commit -> the stage's "empty" mbarrier; after the last K block
 //               tcgen05.commit -> "accumulator ready"
-//   warps 2..5  epilogue: each warp owns the 32 TMEM lanes (= output rows) it may address
-//               (warp_id % 4), tcgen05.ld 32 columns at a time; a thread holds a whole output row, so
-//               bias / GELU / residual / LayerNorm need no cross-thread reduction
+//   warps 2..9  epilogue: two warps per 32 TMEM lanes (= output rows; a warp may address lanes 32 (warp_id % 4) ..),
+//               each taking 64 of the tile's 128 columns, tcgen05.ld 32 columns at a time; a thread holds half an
+//               output row, so bias / GELU / residual need no cross-thread step and LayerNorm exchanges two partial
+//               sums per row with its partner warp through shared memory (named barrier per lane quadrant).  One warp
+//               per scheduler with whole rows (round 1) left the epilogue latency-bound: 39k cycles per tile against
+//               ~5k for loads + MMAs (profiles/r02_decode_kernels_full.txt)
 // Accuracy: hi = cvt.rna.tf32(x), lo = x - hi (exact); dropping lo.lo leaves ~2^-21 relative error
 // per product, accumulated in fp32 in TMEM.
 #include "tc_gemm.cuh"
@@ -32,9 +35,10 @@ constexpr int BM = 128, BN = 128, BK = 32;        // BK fp32 = 128 B = one swizz
 constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4;           // 16 KB (A and W tiles have the same shape)
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // A_hi, A_lo, W_hi, W_lo
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                    // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kTmemCols = 128;
-constexpr int kSmemBytes = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int kRedFloats = 4 * 2 * 128;          // LayerNorm partial sums: [exchange][column half][row]
+constexpr int kSmemBytes = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + kRedFloats * 4;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
@@ -100,21 +104,90 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = x - hi;
 }
 
-__device__ __forceinline__ void row_layernorm128(float (&v)[128], const float* __restrict__ g,
-                                                 const float* __restrict__ b, float eps) {
+// ---- coalescing the epilogue's global traffic.  A thread owns an output ROW (its TMEM lane), so direct loads / stores
+// touch 32 different 128-byte lines per warp instruction: 32 LSU wavefronts for 512 bytes, and the tile's epilogue was
+// bound by exactly that (profiles/r02_decode_kernels_full.txt: 39k cycles per tile, 20k wavefronts).  Instead every
+// warp transposes through its own staging tile in the operand ring (free once the accumulator is complete):
+// [32 rows][W + 4] floats -- row-per-thread float4 accesses and row-contiguous float4 accesses are both conflict-free.
+template <int W>
+__device__ __forceinline__ void stage_put_row(float* stg, int lane, const float (&v)[W]) {
+#pragma unroll
+  for (int i = 0; i < W / 4; ++i)
+    *reinterpret_cast<float4*>(stg + lane * (W + 4) + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+// rows [row0, row0 + 32) x W columns from the staging tile to dst (row stride ld floats), whole 128-byte lines per instruction
+template <int W>
+__device__ __forceinline__ void stage_copy_out(const float* stg, int lane, float* dst, int ld, int rows_valid) {
+  constexpr int LPR = W / 4, RPI = 32 / LPR;   // lanes per row, rows per instruction
+  const int r0 = lane / LPR, c4 = lane % LPR;
+#pragma unroll
+  for (int i = 0; i < 32 / RPI; ++i) {
+    const int r = i * RPI + r0;
+    const float4 x = *reinterpret_cast<const float4*>(stg + r * (W + 4) + 4 * c4);
+    if (r < rows_valid) *reinterpret_cast<float4*>(dst + static_cast<size_t>(r) * ld + 4 * c4) = x;
+  }
+}
+// v -> TF32 hi / lo planes at (row0.., col0..) of C_hi / C_lo
+template <int W>
+__device__ __forceinline__ void store_planes_coalesced(float* stg, int lane, const float (&v)[W], float* c_hi, float* c_lo,
+                                                       int ld, int rows_valid) {
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < W / 4; ++i) {   // hi plane (the split is recomputed for the lo plane: cheaper than 64 more live registers)
+    float4 h, l;
+    split_tf32(v[4 * i + 0], h.x, l.x);
+    split_tf32(v[4 * i + 1], h.y, l.y);
+    split_tf32(v[4 * i + 2], h.z, l.z);
+    split_tf32(v[4 * i + 3], h.w, l.w);
+    *reinterpret_cast<float4*>(stg + lane * (W + 4) + 4 * i) = h;
+  }
+  __syncwarp();
+  stage_copy_out<W>(stg, lane, c_hi, ld, rows_valid);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < W / 4; ++i) {
+    float4 h, l;
+    split_tf32(v[4 * i + 0], h.x, l.x);
+    split_tf32(v[4 * i + 1], h.y, l.y);
+    split_tf32(v[4 * i + 2], h.z, l.z);
+    split_tf32(v[4 * i + 3], h.w, l.w);
+    *reinterpret_cast<float4*>(stg + lane * (W + 4) + 4 * i) = l;
+  }
+  __syncwarp();
+  stage_copy_out<W>(stg, lane, c_lo, ld, rows_valid);
+}
+
+__device__ __forceinline__ void bar_pair(int q) { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); }
+
+// LayerNorm of a 128-wide row held as two halves of 64 by the two epilogue warps of a lane quadrant (two-pass mean /
+// biased variance); `red` = [2 exchanges][2 halves][128 rows] floats.  g, b point at this half's 64 entries.
+__device__ __forceinline__ void row_layernorm_halves(float (&v)[64], const float* __restrict__ g, const float* __restrict__ b,
+                                                     float eps, float* red, int half, int row, int q) {
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 128; ++i) s += v[i];
-  const float mean = s * (1.0f / 128.0f);
-  float q = 0.f;
+  for (int i = 0; i < 64; ++i) s += v[i];
+  red[half * 128 + row] = s;
+  bar_pair(q);
+  const float mean = (red[row] + red[128 + row]) * (1.0f / 128.0f);
+  float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < 128; ++i) {
+  for (int i = 0; i < 64; ++i) {
     v[i] -= mean;
-    q = fmaf(v[i], v[i], q);
+    sq = fmaf(v[i], v[i], sq);
   }
-  const float rstd = rsqrtf(q * (1.0f / 128.0f) + eps);
+  red[256 + half * 128 + row] = sq;
+  bar_pair(q);
+  const float rstd = rsqrtf((red[256 + row] + red[384 + row]) * (1.0f / 128.0f) + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
 #pragma unroll
-  for (int i = 0; i < 128; ++i) v[i] = v[i] * rstd * __ldg(g + i) + __ldg(b + i);
+  for (int i = 0; i < 16; ++i) {
+    const float4 gg = __ldg(g4 + i), bb = __ldg(b4 + i);
+    v[4 * i + 0] = v[4 * i + 0] * rstd * gg.x + bb.x;
+    v[4 * i + 1] = v[4 * i + 1] * rstd * gg.y + bb.y;
+    v[4 * i + 2] = v[4 * i + 2] * rstd * gg.z + bb.z;
+    v[4 * i + 3] = v[4 * i + 3] * rstd * gg.w + bb.w;
+  }
 }
 
 }  // namespace
@@ -132,6 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* empty = bars + STAGES;       // [STAGES]
   uint64_t* acc_ready = bars + 2 * STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  float* red = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // blockIdx.x walks the N tiles of one M block: the CTAs that share an A tile are launched together, so
@@ -212,58 +286,81 @@ __global__ void __launch_bounds__(kThreads, 1)
       __syncwarp();
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;                // TMEM lanes [32q, 32q+32) are the ones this warp may access
+    const int half = (warp - 2) >> 2;      // my 64 of the tile's 128 columns
     const int m = m0 + q * 32 + lane;      // my output row
     const bool row_ok = m < d.M;
+    const int rows_valid = d.M - (m0 + q * 32);                         // of my warp's 32 rows (may exceed 32)
+    float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 68);   // my staging tile (operand ring, after acc_ready)
+    // LayerNorm epilogues: the residual rows (hi + lo) of my 32 x 64 block, fetched with whole-line loads while the
+    // mainloop runs (the epilogue warps are idle until the accumulator is complete)
+    float4 rr[(EPI == EPI_RES_LN_PLANES || EPI == EPI_RES_LN_CROSS_LN_PLANES) ? 16 : 1];
+    if (EPI == EPI_RES_LN_PLANES || EPI == EPI_RES_LN_CROSS_LN_PLANES) {
+      const int r0 = lane >> 4, c4 = lane & 15;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int r = 2 * i + r0;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (r < rows_valid) {
+          const size_t off = static_cast<size_t>(m0 + q * 32 + r) * d.ldr + half * 64 + 4 * c4;
+          a = __ldg(reinterpret_cast<const float4*>(d.R_hi + off));
+          b = __ldg(reinterpret_cast<const float4*>(d.R_lo + off));
+        }
+        rr[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      }
+    }
     mbar_wait(acc_ready, 0);
     tc_fence_after();
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 
     if (EPI == EPI_RES_LN_PLANES || EPI == EPI_RES_LN_CROSS_LN_PLANES) {
-      float v[128];
+      float v[64];
+      const int c0 = half * 64;            // N == 128: the tile is the whole row
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         float t[32];
-        tmem_ld32(trow + c * 32, t);
+        tmem_ld32(trow + c0 + c * 32, t);
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[c * 32 + i] = t[i];
       }
       const size_t mr = row_ok ? m : 0;
-      const float4* rh = reinterpret_cast<const float4*>(d.R_hi + mr * d.ldr);
-      const float4* rl = reinterpret_cast<const float4*>(d.R_lo + mr * d.ldr);
+      const int row = q * 32 + lane;
+      {
+        const int r0 = lane >> 4, c4 = lane & 15;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float4 a = __ldg(rh + i), b = __ldg(rl + i);
-        v[i * 4 + 0] += __ldg(d.bias + i * 4 + 0) + (a.x + b.x);
-        v[i * 4 + 1] += __ldg(d.bias + i * 4 + 1) + (a.y + b.y);
-        v[i * 4 + 2] += __ldg(d.bias + i * 4 + 2) + (a.z + b.z);
-        v[i * 4 + 3] += __ldg(d.bias + i * 4 + 3) + (a.w + b.w);
+        for (int i = 0; i < 16; ++i) *reinterpret_cast<float4*>(stg + (2 * i + r0) * 68 + 4 * c4) = rr[i];
       }
-      row_layernorm128(v, d.ln_g, d.ln_b, d.ln_eps);
+      __syncwarp();
+      const float4* b4 = reinterpret_cast<const float4*>(d.bias + c0);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float4 r4 = *reinterpret_cast<const float4*>(stg + lane * 68 + 4 * i), bi = __ldg(b4 + i);
+        v[i * 4 + 0] += bi.x + r4.x;
+        v[i * 4 + 1] += bi.y + r4.y;
+        v[i * 4 + 2] += bi.z + r4.z;
+        v[i * 4 + 3] += bi.w + r4.w;
+      }
+      row_layernorm_halves(v, d.ln_g + c0, d.ln_b + c0, d.ln_eps, red, half, row, q);
       if (EPI == EPI_RES_LN_CROSS_LN_PLANES) {
-        const float* cv = d.cvec + static_cast<size_t>(mr / d.rows_per_clip) * 128;
+        const float4* cv = reinterpret_cast<const float4*>(d.cvec + static_cast<size_t>(mr / d.rows_per_clip) * 128 + c0);
 #pragma unroll
-        for (int i = 0; i < 128; ++i) v[i] += __ldg(cv + i);
-        row_layernorm128(v, d.ln2_g, d.ln2_b, d.ln_eps);
-      }
-      if (row_ok) {
-        float4* oh = reinterpret_cast<float4*>(d.C_hi + static_cast<size_t>(m) * d.ldc);
-        float4* ol = reinterpret_cast<float4*>(d.C_lo + static_cast<size_t>(m) * d.ldc);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float4 h, l;
-          split_tf32(v[i * 4 + 0], h.x, l.x);
-          split_tf32(v[i * 4 + 1], h.y, l.y);
-          split_tf32(v[i * 4 + 2], h.z, l.z);
-          split_tf32(v[i * 4 + 3], h.w, l.w);
-          oh[i] = h;
-          ol[i] = l;
+        for (int i = 0; i < 16; ++i) {
+          const float4 c4 = __ldg(cv + i);
+          v[i * 4 + 0] += c4.x;
+          v[i * 4 + 1] += c4.y;
+          v[i * 4 + 2] += c4.z;
+          v[i * 4 + 3] += c4.w;
         }
+        row_layernorm_halves(v, d.ln2_g + c0, d.ln2_b + c0, d.ln_eps, red + 512, half, row, q);
+      }
+      {
+        const size_t off = static_cast<size_t>(m0 + q * 32) * d.ldc + c0;
+        store_planes_coalesced<64>(stg, lane, v, d.C_hi + off, d.C_lo + off, d.ldc, rows_valid);
       }
     } else {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half * 2; c < half * 2 + 2; ++c) {
         const int nc = n0 + c * 32;
         if (nc >= d.N) break;                    // warp-uniform
         float v[32];
@@ -293,8 +390,8 @@ __global__ void __launch_bounds__(kThreads, 1)
             v[i * 4 + 3] += a.w + b.w;
           }
         }
-        if (!row_ok) continue;
         if (EPI == EPI_QKV_HEADS) {
+          if (row_ok) {
           const int D = d.heads * 64;
           const int which = nc / D, rem = nc - which * D, hd = rem >> 6, d0 = rem & 63;   // warp-uniform
           const int b = m / d.tok, t = m - b * d.tok;
@@ -327,30 +424,22 @@ __global__ void __launch_bounds__(kThreads, 1)
               d.vt_lo[off + static_cast<size_t>(i) * d.tokp] = l;
             }
           }
+          }
         } else if (EPI == EPI_PLAIN || EPI == EPI_QKV) {
-          float* dst = d.C + static_cast<size_t>(m) * d.ldc + nc;
           if (nc + 32 <= d.N && (d.ldc & 3) == 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              reinterpret_cast<float4*>(dst)[i] = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
-          } else {
+            __syncwarp();
+            stage_put_row<32>(stg, lane, v);
+            __syncwarp();
+            stage_copy_out<32>(stg, lane, d.C + static_cast<size_t>(m0 + q * 32) * d.ldc + nc, d.ldc, rows_valid);
+          } else if (row_ok) {
+            float* dst = d.C + static_cast<size_t>(m) * d.ldc + nc;
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (nc + i < d.N) dst[i] = v[i];
           }
         } else {
-          float4* oh = reinterpret_cast<float4*>(d.C_hi + static_cast<size_t>(m) * d.ldc + nc);
-          float4* ol = reinterpret_cast<float4*>(d.C_lo + static_cast<size_t>(m) * d.ldc + nc);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 h, l;
-            split_tf32(v[i * 4 + 0], h.x, l.x);
-            split_tf32(v[i * 4 + 1], h.y, l.y);
-            split_tf32(v[i * 4 + 2], h.z, l.z);
-            split_tf32(v[i * 4 + 3], h.w, l.w);
-            oh[i] = h;
-            ol[i] = l;
-          }
+          const size_t off = static_cast<size_t>(m0 + q * 32) * d.ldc + nc;
+          store_planes_coalesced<32>(stg, lane, v, d.C_hi + off, d.C_lo + off, d.ldc, rows_valid);
         }
       }
     }

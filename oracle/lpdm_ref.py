@@ -377,6 +377,29 @@ def geodesic_deg(aa_a: Tensor, aa_b: Tensor) -> Tensor:
     return torch.rad2deg(torch.acos(tr.clamp(-1, 1)))
 
 
+def gram_schmidt_cond(feats: Tensor) -> Tensor:
+    """1 / min(|a1|, |a2 - (b1.a2) b1|) per rotation: how much Gram-Schmidt (dm/utils/transforms.py:141-160) amplifies an
+    error of the 6D features into an error of the rotation.  [..., 333] -> [..., 55]."""
+    d6 = feats[..., :330].double().reshape(*feats.shape[:-1], 55, 6)
+    a1, a2 = d6[..., :3], d6[..., 3:]
+    n1 = a1.norm(dim=-1)
+    b1 = a1 / n1[..., None]
+    n2 = (a2 - (b1 * a2).sum(-1, keepdim=True) * b1).norm(dim=-1)
+    return 1.0 / torch.minimum(n1, n2)
+
+
+def check_poses(poses: Tensor, ref_poses: Tensor, ref_feats: Tensor, feats_err: float, tol_deg: float = 0.05):
+    """Pose parity through the rotation geodesic, conditioning-aware: a rotation whose 6D vectors are short is
+    ill-conditioned (synthetic weights give |a| down to ~0.01), so its bound is the measured 6D feature error carried
+    through the conditioning of Gram-Schmidt; well-conditioned rotations (cond < 4) must meet `tol_deg`.
+    Returns (ok, geodesic max, well-conditioned geodesic max)."""
+    geo = geodesic_deg(poses, ref_poses)
+    cond = gram_schmidt_cond(ref_feats)
+    bound = torch.rad2deg(3.0 * feats_err * 6 ** 0.5 * cond) + 0.01
+    well = geo[cond < 4].max().item() if bool((cond < 4).any()) else 0.0
+    return bool((geo <= bound).all()) and well < tol_deg, geo.max().item(), well
+
+
 # --------------------------------------------------------------------------- whole path
 def diffusion_backward(den_sd: SD, vae_sd: SD, latents0: Tensor, con: Tensor, emo: Optional[Tensor],
                        sty: Optional[Tensor], n_steps: int = 50, sampler: str = "ddim",

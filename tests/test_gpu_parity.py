@@ -27,15 +27,7 @@ def _t(a):
     return torch.from_numpy(np.asarray(a))
 
 
-def _gram_schmidt_cond(feats64):
-    """1 / min(|a1|, |a2 - (b1.a2) b1|) per rotation: how much Gram-Schmidt (dm/utils/transforms.py:141-160)
-    amplifies an error of the 6D features into an error of the rotation."""
-    d6 = feats64[..., :330].double().reshape(*feats64.shape[:-1], 55, 6)
-    a1, a2 = d6[..., :3], d6[..., 3:]
-    n1 = a1.norm(dim=-1)
-    b1 = a1 / n1[..., None]
-    n2 = (a2 - (b1 * a2).sum(-1, keepdim=True) * b1).norm(dim=-1)
-    return 1.0 / torch.minimum(n1, n2)
+_gram_schmidt_cond = R.gram_schmidt_cond
 
 
 def _assert_poses(name, poses, poses32, poses64, feats64, feats_err):

@@ -34,3 +34,24 @@ def test_erf_fast_is_sub_ulp():
     ulp = np.spacing(np.abs(ref).astype(np.float32)).astype(np.float64)
     assert err.max() < 1e-7
     assert (err / ulp).max() < 1.5
+
+
+def test_check_poses_is_conditioning_aware():
+    """oracle/lpdm_ref.py::check_poses (used by smoke() and the setup test): the feature error explains the pose error of
+    ill-conditioned 6D pairs, a well-conditioned rotation that is off by more than the tolerance fails."""
+    import torch
+    from oracle import lpdm_ref as R
+    g = torch.Generator().manual_seed(0)
+    feats = torch.randn(2, 4, 333, generator=g)
+    feats[0, 0, :6] *= 0.01                                     # one ill-conditioned joint (|a| ~ 0.01)
+    ref = R.feats_to_motion(feats)
+    ok, geo, well = R.check_poses(ref["poses"], ref["poses"], feats, 1e-6)
+    assert ok and geo < 1e-3 and well < 1e-3
+    noisy = feats + 1e-5 * torch.randn(feats.shape, generator=g)
+    got = R.feats_to_motion(noisy)
+    ok, geo, well = R.check_poses(got["poses"], ref["poses"], feats, 4e-5)
+    assert ok and well < 0.05
+    bad = feats.clone()
+    bad[1, 1, 6:12] += 0.05                                     # a well-conditioned joint moved by degrees
+    got = R.feats_to_motion(bad)
+    assert not R.check_poses(got["poses"], ref["poses"], feats, 1e-5)[0]
