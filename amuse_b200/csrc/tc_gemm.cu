@@ -104,58 +104,9 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = x - hi;
 }
 
-// ---- coalescing the epilogue's global traffic.  A thread owns an output ROW (its TMEM lane), so direct loads / stores
-// touch 32 different 128-byte lines per warp instruction: 32 LSU wavefronts for 512 bytes, and the tile's epilogue was
-// bound by exactly that (profiles/r02_decode_kernels_full.txt: 39k cycles per tile, 20k wavefronts).  Instead every
-// warp transposes through its own staging tile in the operand ring (free once the accumulator is complete):
-// [32 rows][W + 4] floats -- row-per-thread float4 accesses and row-contiguous float4 accesses are both conflict-free.
-template <int W>
-__device__ __forceinline__ void stage_put_row(float* stg, int lane, const float (&v)[W]) {
-#pragma unroll
-  for (int i = 0; i < W / 4; ++i)
-    *reinterpret_cast<float4*>(stg + lane * (W + 4) + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-}
-// rows [row0, row0 + 32) x W columns from the staging tile to dst (row stride ld floats), whole 128-byte lines per instruction
-template <int W>
-__device__ __forceinline__ void stage_copy_out(const float* stg, int lane, float* dst, int ld, int rows_valid) {
-  constexpr int LPR = W / 4, RPI = 32 / LPR;   // lanes per row, rows per instruction
-  const int r0 = lane / LPR, c4 = lane % LPR;
-#pragma unroll
-  for (int i = 0; i < 32 / RPI; ++i) {
-    const int r = i * RPI + r0;
-    const float4 x = *reinterpret_cast<const float4*>(stg + r * (W + 4) + 4 * c4);
-    if (r < rows_valid) *reinterpret_cast<float4*>(dst + static_cast<size_t>(r) * ld + 4 * c4) = x;
-  }
-}
-// v -> TF32 hi / lo planes at (row0.., col0..) of C_hi / C_lo
-template <int W>
-__device__ __forceinline__ void store_planes_coalesced(float* stg, int lane, const float (&v)[W], float* c_hi, float* c_lo,
-                                                       int ld, int rows_valid) {
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < W / 4; ++i) {   // hi plane (the split is recomputed for the lo plane: cheaper than 64 more live registers)
-    float4 h, l;
-    split_tf32(v[4 * i + 0], h.x, l.x);
-    split_tf32(v[4 * i + 1], h.y, l.y);
-    split_tf32(v[4 * i + 2], h.z, l.z);
-    split_tf32(v[4 * i + 3], h.w, l.w);
-    *reinterpret_cast<float4*>(stg + lane * (W + 4) + 4 * i) = h;
-  }
-  __syncwarp();
-  stage_copy_out<W>(stg, lane, c_hi, ld, rows_valid);
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < W / 4; ++i) {
-    float4 h, l;
-    split_tf32(v[4 * i + 0], h.x, l.x);
-    split_tf32(v[4 * i + 1], h.y, l.y);
-    split_tf32(v[4 * i + 2], h.z, l.z);
-    split_tf32(v[4 * i + 3], h.w, l.w);
-    *reinterpret_cast<float4*>(stg + lane * (W + 4) + 4 * i) = l;
-  }
-  __syncwarp();
-  stage_copy_out<W>(stg, lane, c_lo, ld, rows_valid);
-}
+using tcp::stage_copy_out;
+using tcp::stage_put_row;
+using tcp::store_planes_coalesced;
 
 __device__ __forceinline__ void bar_pair(int q) { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); }
 

@@ -16,7 +16,8 @@
 //               12 tcgen05.mma.cta_group::2.kind::tf32 (M256 N256 K8) per K block and multicasts
 //               tcgen05.commit to both CTAs' "empty" / "accumulator full" barriers
 //   warps 2..5  epilogue on the CTA's own 128 accumulator rows, overlapped with the next tile's main
-//               loop through the second accumulator buffer; one output row per thread
+//               loop through the second accumulator buffer; one output row per thread, global loads / stores
+//               transposed through per-warp staging tiles so that they move whole 128-byte lines
 #include <cudaTypedefs.h>
 
 #include "common.cuh"
@@ -39,11 +40,20 @@ constexpr int STAGE_BYTES = 4 * TILE_BYTES;     // A_hi, A_lo, W_hi, W_lo  (per 
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 512;                  // 2 accumulator buffers x 256 columns
 constexpr int kBarOff = STAGES * STAGE_BYTES;
-constexpr int kSmemBytes = kBarOff + 256 + 1024;
+constexpr int kStageOff = kBarOff + 256;         // 4 epilogue warps x [32 rows][36] floats: the transposing staging tiles
+constexpr int kSmemBytes = kStageOff + 4 * 32 * 36 * 4 + 1024;
 constexpr uint32_t kIdesc = idesc_tf32(2 * BM, BN);
 
+// Epilogue of one 32-column chunk of my warp's 32 rows.  A thread owns a ROW of the accumulator, so all global traffic
+// is transposed through the warp's staging tile (tc_ptx.cuh: stage_*): whole 128-byte lines per instruction instead of
+// 32 lines x 16 bytes -- at K = 768 the epilogue's LSU wavefronts, not the MMAs, bounded the tile (proj GEMM 54 %
+// tensor-active, profiles/r01_ast_kernels_full.txt).  `res` = this chunk's residual (hi + lo), fetched one chunk ahead
+// in the staging layout (row 4 i + lane / 8, columns 4 (lane % 8) ..).
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmDesc& d, int m, bool row_ok, int nc, float (&v)[32]) {
+__device__ __forceinline__ void epilogue_chunk(const GemmDesc& d, int row0, int rows_valid, int lane, int nc, float (&v)[32],
+                                               float* stg, const float4 (&res)[8]) {
+  const int m = row0 + lane;
+  const bool row_ok = lane < rows_valid;
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] += __ldg(d.bias + nc + i);
   if (EPI == EPI_GELU_PLANES) {
@@ -51,44 +61,40 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDesc& d, int m, bool ro
     for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
   }
   if (EPI == EPI_RES_PLANES) {
-    const size_t mr = row_ok ? m : 0;
-    const float4* rh = reinterpret_cast<const float4*>(d.R_hi + mr * d.ldr + nc);
-    const float4* rl = reinterpret_cast<const float4*>(d.R_lo + mr * d.ldr + nc);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(stg + (4 * i + (lane >> 3)) * 36 + 4 * (lane & 7)) = res[i];
+    __syncwarp();
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float4 a = rh[i], b = rl[i];   // plain loads: C may alias R (in-place residual update)
-      v[i * 4 + 0] += a.x + b.x;
-      v[i * 4 + 1] += a.y + b.y;
-      v[i * 4 + 2] += a.z + b.z;
-      v[i * 4 + 3] += a.w + b.w;
+      const float4 r4 = *reinterpret_cast<const float4*>(stg + lane * 36 + 4 * i);
+      v[i * 4 + 0] += r4.x;
+      v[i * 4 + 1] += r4.y;
+      v[i * 4 + 2] += r4.z;
+      v[i * 4 + 3] += r4.w;
     }
   }
-  if (!row_ok) return;
   if (EPI == EPI_QKV_HEADS) {
     const int D = d.heads * 64;
     const int which = nc / D, rem = nc - which * D, hd = rem >> 6, d0 = rem & 63;   // warp-uniform
-    const int b = m / d.tok, t = m - b * d.tok;
-    const size_t bh = static_cast<size_t>(b) * d.heads + hd;
     if (which == 0) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] *= d.q_scale;
     }
-    if (which < 2) {
-      const size_t off = (bh * d.tokp + t) * 64 + d0;
-      float4* oh = reinterpret_cast<float4*>((which == 0 ? d.q_hi : d.k_hi) + off);
-      float4* ol = reinterpret_cast<float4*>((which == 0 ? d.q_lo : d.k_lo) + off);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 h, l;
-        split_tf32(v[i * 4 + 0], h.x, l.x);
-        split_tf32(v[i * 4 + 1], h.y, l.y);
-        split_tf32(v[i * 4 + 2], h.z, l.z);
-        split_tf32(v[i * 4 + 3], h.w, l.w);
-        oh[i] = h;
-        ol[i] = l;
-      }
-    } else {   // v transposed: consecutive lanes = consecutive tokens -> coalesced 128-B stores
-      const size_t off = (bh * 64 + d0) * d.tokp + t;
+    if (which < 2) {   // q / k planes [clip x head][token][64]: a warp's rows may straddle two clips -> per-row pointers
+      float* const ph = which == 0 ? d.q_hi : d.k_hi;
+      float* const pl = which == 0 ? d.q_lo : d.k_lo;
+      auto off_of = [&](int r) -> long long {
+        if (r >= rows_valid) return -1;
+        const int mr = row0 + r, b = mr / d.tok, t = mr - b * d.tok;
+        return static_cast<long long>((static_cast<size_t>(b) * d.heads + hd) * d.tokp + t) * 64 + d0;
+      };
+      store_planes_coalesced_rows<32>(
+          stg, lane, v, [&](int r) { const long long o = off_of(r); return o < 0 ? nullptr : ph + o; },
+          [&](int r) { const long long o = off_of(r); return o < 0 ? nullptr : pl + o; });
+    } else if (row_ok) {   // v transposed: consecutive lanes = consecutive tokens -> coalesced 128-B stores
+      const int b = m / d.tok, t = m - b * d.tok;
+      const size_t off = ((static_cast<size_t>(b) * d.heads + hd) * 64 + d0) * d.tokp + t;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         float h, l;
@@ -98,22 +104,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDesc& d, int m, bool ro
       }
     }
   } else if (EPI == EPI_PLAIN) {
-    float4* dst = reinterpret_cast<float4*>(d.C + static_cast<size_t>(m) * d.ldc + nc);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+    __syncwarp();
+    stage_put_row<32>(stg, lane, v);
+    __syncwarp();
+    stage_copy_out<32>(stg, lane, d.C + static_cast<size_t>(row0) * d.ldc + nc, d.ldc, rows_valid);
   } else {
-    float4* oh = reinterpret_cast<float4*>(d.C_hi + static_cast<size_t>(m) * d.ldc + nc);
-    float4* ol = reinterpret_cast<float4*>(d.C_lo + static_cast<size_t>(m) * d.ldc + nc);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 h, l;
-      split_tf32(v[i * 4 + 0], h.x, l.x);
-      split_tf32(v[i * 4 + 1], h.y, l.y);
-      split_tf32(v[i * 4 + 2], h.z, l.z);
-      split_tf32(v[i * 4 + 3], h.w, l.w);
-      oh[i] = h;
-      ol[i] = l;
-    }
+    const size_t off = static_cast<size_t>(row0) * d.ldc + nc;
+    store_planes_coalesced<32>(stg, lane, v, d.C_hi + off, d.C_lo + off, d.ldc, rows_valid);
   }
 }
 
@@ -220,12 +217,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     // ===================== epilogue (warps 2..5, both CTAs) =====================
     const int q = warp & 3;                // TMEM lanes [32q, 32q+32) are the ones this warp may access
     const uint32_t ae0 = map_to_rank(&acc_empty[0], 0), ae1 = map_to_rank(&acc_empty[1], 0);
+    float* stg = reinterpret_cast<float*>(smem + kStageOff) + (warp - 2) * (32 * 36);
+    float4 res[8];                         // EPI_RES_PLANES: the residual of the chunk about to be processed
+    auto load_res = [&](int row0, int rows_valid, int nc) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = 4 * i + (lane >> 3);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (r < rows_valid) {   // plain loads: C may alias R (in-place residual update; this warp owns these rows / columns)
+          const size_t off = static_cast<size_t>(row0 + r) * d.ldr + nc + 4 * (lane & 7);
+          a = *reinterpret_cast<const float4*>(d.R_hi + off);
+          b = *reinterpret_cast<const float4*>(d.R_lo + off);
+        }
+        res[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      }
+    };
     uint32_t lt = 0;
     for (int tile = pair; tile < n_tiles; tile += n_pairs, ++lt) {
       const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
-      const int m = tm * (2 * BM) + static_cast<int>(rank) * BM + q * 32 + lane;   // my output row
-      const bool row_ok = m < d.M;
+      const int row0 = tm * (2 * BM) + static_cast<int>(rank) * BM + q * 32;   // my warp's first output row
+      const int rows_valid = d.M - row0;
       const uint32_t buf = lt & 1;
+      if (EPI == EPI_RES_PLANES) load_res(row0, rows_valid, tn * BN);   // under the tile's MMAs
       mbar_wait(&acc_full[buf], (lt >> 1) & 1);
       tc_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
@@ -238,7 +251,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(buf ? ae1 : ae0);
         }
-        epilogue_chunk<EPI>(d, m, row_ok, tn * BN + c * 32, v);
+        float4 cur[8];
+        if (EPI == EPI_RES_PLANES) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cur[i] = res[i];
+          if (c + 1 < BN / 32) load_res(row0, rows_valid, tn * BN + (c + 1) * 32);   // next chunk's, under this chunk's work
+        }
+        epilogue_chunk<EPI>(d, row0, rows_valid, lane, tn * BN + c * 32, v, stg, cur);
       }
     }
     tc_fence_before();

@@ -26,6 +26,9 @@ if what in ("denoise", "decode"):
     else:
         poses, trans = eng.decode(l0)
         print("poses", float(poses.abs().max()))
+        feats = eng.motion_to_feats(poses[:2].contiguous(), trans[:2].contiguous())   # the encoder: 302-token attention
+        mu, logvar = eng.encode(feats)
+        print("mu", float(mu.abs().max()))
 elif what == "ast":
     eng.load_state_dict("ast", W.ast_state_dict(depth=1))
     eng.finalize()
