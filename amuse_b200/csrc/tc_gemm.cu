@@ -382,11 +382,12 @@ __global__ void __launch_bounds__(kThreads, 1)
             stage_put_row<32>(stg, lane, v);
             __syncwarp();
             stage_copy_out<32>(stg, lane, d.C + static_cast<size_t>(m0 + q * 32) * d.ldc + nc, d.ldc, rows_valid);
-          } else if (row_ok) {
-            float* dst = d.C + static_cast<size_t>(m) * d.ldc + nc;
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (nc + i < d.N) dst[i] = v[i];
+          } else {   // the 333-wide feature rows of the final projection: unaligned rows, ragged last chunk
+            __syncwarp();
+            stage_put_row<32>(stg, lane, v);
+            __syncwarp();
+            tcp::stage_copy_out_scalar32(stg, lane, d.C + static_cast<size_t>(m0 + q * 32) * d.ldc + nc, d.ldc, rows_valid,
+                                         d.N - nc);
           }
         } else {
           const size_t off = static_cast<size_t>(m0 + q * 32) * d.ldc + nc;

@@ -235,6 +235,16 @@ __device__ __forceinline__ void store_planes_coalesced(float* stg, int lane, con
   stage_copy_out<W>(stg, lane, c_lo, ld, rows_valid);
 }
 
+// rows x 32 columns with no alignment or edge assumption (ld not a multiple of 4, N edge): a warp writes one row's 32
+// consecutive floats per instruction
+__device__ __forceinline__ void stage_copy_out_scalar32(const float* stg, int lane, float* dst, int ld, int rows_valid,
+                                                        int cols_valid) {
+  if (lane < cols_valid) {
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r)
+      if (r < rows_valid) dst[static_cast<size_t>(r) * ld + lane] = stg[r * 36 + lane];
+  }
+}
 // the same with a row -> pointer map (rows of a warp that land in different output blocks; nullptr = skip the row)
 template <int W, class RowPtr>
 __device__ __forceinline__ void stage_copy_out_rows(const float* stg, int lane, RowPtr rowptr) {
