@@ -45,7 +45,7 @@ for l in sass.splitlines():
                 counts[cur][k] += 1
 print(f"# {LIB.relative_to(ROOT)}: {len(counts)} kernels (nvcc -gencode arch=compute_100a,code=sm_100a)")
 for fn, c in counts.items():
-    name = re.sub(r"\(.*", "", demangle(fn))
+    name = re.sub(r"\(.*", "", demangle(fn).replace("(anonymous namespace)::", ""))
     print(f"\n{name}")
     print(f"  {usage.get(fn, '')}")
     print("  instr=%d  " % c["instr"] + "  ".join(f"{k}={c[k]}" for k in PAT if c[k]))
