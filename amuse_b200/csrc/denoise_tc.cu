@@ -168,7 +168,6 @@ struct Ctx {
   __device__ __forceinline__ uint64_t* empty(uint32_t s) const { return bars + 3 + s; }
   __device__ __forceinline__ uint64_t* dbar(int i) const { return bars + 6 + i; }
   __device__ __forceinline__ uint64_t* xbar(uint32_t i) const { return bars + 8 + i; }
-  __device__ __forceinline__ uint64_t* bready() const { return bars + 10; }
   __device__ __forceinline__ uint64_t* sfull(int i) const { return bars + 11 + i; }    // side slots: the two out_proj tiles
   __device__ __forceinline__ uint64_t* sempty(int i) const { return bars + 13 + i; }
 };
@@ -327,7 +326,7 @@ __device__ __forceinline__ void issuer_loop(const Ctx& k) {
   const bool prof_cta = (p.prof != nullptr) && cluster_id_x() == 0 && cluster_ctarank() == 0;
   const uint64_t dBx = umma_desc(smem_u32(k.smem + oBx)), dBo = umma_desc(smem_u32(k.smem + oBo)),
                  dBh = umma_desc(smem_u32(k.smem + oBh));
-  uint32_t slot = 0, use = 0, suse = 0, bph = 0;
+  uint32_t slot = 0, use = 0, suse = 0;
   for (int step = 0; step < p.n_steps; ++step) {
     for (int stage = 0; stage < kTilesPerStep; ++stage) {
       const int kind = c_tiles[stage].x;
@@ -348,8 +347,7 @@ __device__ __forceinline__ void issuer_loop(const Ctx& k) {
         wait_bar(k, k.full(slot), use & 1);
         wait_bar(k, k.full(s2), u2 & 1);
       }
-      wait_bar(k, k.bready(), bph);
-      bph ^= 1;
+      asm volatile("bar.sync 4, 288;" ::: "memory");   // "B operand ready": all 8 epilogue warps have arrived (signal_b)
       tc_fence_after();
       const bool fine = prof_cta && step == p.prof_step && (stage == 5 || stage == 6);
       if (fine && elect_one()) p.prof[stage == 5 ? 108 : 112] = clock64();
@@ -440,23 +438,19 @@ struct Chain {
       }
   }
 
-  // Waiting for an mbarrier: ONE warp per group polls it, the group's other three warps block on the group's named
-  // barrier (a hardware wait that issues nothing).  Probing warps execute instructions: with all 8 epilogue warps
-  // polling, the probes were 17% of everything the SM issued (profiles/r02_denoise_tc_lines.txt, first capture).
-#ifndef AMUSE_DN2_ALL_POLL
-  __device__ __forceinline__ void wait_group(uint64_t* bar, uint32_t parity) const {
-    if (q == 0) wait_bar(k, bar, parity);
-    bar_group();
-  }
-#else
+  // Waiting for an mbarrier: every epilogue warp polls it itself.  (Mid-round, with the MMA issuer polling "B ready" on
+  // the same schedulers, one poller per group + a named barrier for the other three was as fast and issued less; with
+  // the issuer blocked on a hardware barrier instead, the extra hop costs 2.7 %: 56.5 -> 55.0 us/step, same box.)
   __device__ __forceinline__ void wait_group(uint64_t* bar, uint32_t parity) const { wait_bar(k, bar, parity); }
-#endif
   // "my part of the B operand is written, and I am done with the accumulators": one arrive per warp
   __device__ __forceinline__ void signal_b() const {
     fence_proxy_async();   // my B-operand stores -> async proxy
     tc_fence_before();     // my tcgen05.ld of the previous accumulator -> before the MMAs that overwrite it
-    __syncwarp();
-    if (lane == 0) mbar_arrive(k.bready());
+    // hardware named barrier 4 = 8 epilogue warps (arrive, non-blocking) + the issuer warp (sync): 2.3 % faster than an
+    // mbarrier arrive per warp + the issuer's try_wait loop (the hop is on the critical path of all 41 stages, and a
+    // blocked issuer issues nothing).  At most one phase is outstanding: no epilogue warp reaches the next signal_b before
+    // the issuer has passed this one (its MMAs produce what they wait for).
+    asm volatile("bar.arrive 4, 288;" ::: "memory");
   }
   // N-split stage: accumulator i (the tile of weight rank 2 rank + i) as soon as ITS MMAs have committed, my group's rows;
   // the epilogue of tile 0 runs under the MMAs of tile 1
@@ -518,7 +512,7 @@ struct Chain {
   // The moments go through one of three shared-memory buffers: LayerNorm 1 and 2 of a layer alternate between two (a
   // warp may write the moments of the next LayerNorm while a slower warp of its group still reads the previous ones only
   // if nothing separates the two -- every pair of consecutive LayerNorms of a layer is separated by a GEMM stage, i.e.
-  // by the bready / accumulator mbarriers, but the final encoder.norm follows LayerNorm 2 of the last layer directly:
+  // by the B-ready barrier / accumulator mbarriers, but the final encoder.norm follows LayerNorm 2 of the last layer directly:
   // compute-sanitizer racecheck flagged exactly that write-after-read), the final norm has its own.
   template <int NR>
   __device__ __forceinline__ void layernorm(float (&v)[kNR], float gam, float bet, int buf) const {
@@ -860,7 +854,6 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     mbar_init(k.dbar(1), 1);
     mbar_init(k.xbar(0), 1);
     mbar_init(k.xbar(1), 1);
-    mbar_init(k.bready(), kChainWarps);
     for (int i = 0; i < kVirt; ++i) {
       mbar_init(k.sfull(i), kProdWarps);
       mbar_init(k.sempty(i), 1);
