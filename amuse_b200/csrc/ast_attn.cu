@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                          const float* __restrict__ q_hi, const float* __restrict__ q_lo, float* __restrict__ o_hi,
                          float* __restrict__ o_lo) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);
   uint64_t* q_ready = bars;                  // [1]  softmax warps -> MMA: Q_hi / Q_lo of both tiles are in TMEM
   uint64_t* s_full = bars + 1;               // [2]  MMA -> softmax t: S_t(j) complete (and PV_t(j-1) before it)

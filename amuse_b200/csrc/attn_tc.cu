@@ -125,7 +125,7 @@ __device__ __forceinline__ void store_row_chunk(uint8_t* base, int row, int c4, 
 __global__ void __launch_bounds__(kAttnThreads, 1)
 self_attention_tc_kernel(const float* __restrict__ qkv, float* __restrict__ out_hi, float* __restrict__ out_lo, int frames) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint64_t* sbar = reinterpret_cast<uint64_t*>(smem + oBar);
   uint64_t* obar = sbar + 1;
   uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + oBar + 16);

@@ -82,6 +82,13 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
       : "memory");
 }
 
+// The dynamic shared-memory window rounded up to 1024 bytes (SWIZZLE_128B operands).  Pointer arithmetic on the
+// __shared__ array itself: rounding through uintptr_t turns every later access into a GENERIC load / store (LD.E / ST.E
+// with 64-bit addresses -- the tcgen05 sampler loop had 120 of them and not one LDS / STS).
+__device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* smem_raw) {
+  return smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+}
+
 // ---- thread-block-cluster primitives ------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -122,7 +122,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                     const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                     const GemmDesc d, const int tiles_m, const int tiles_n) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);
   uint64_t* full = bars;                  // [STAGES]  used in the leader: bytes of both CTAs
   uint64_t* empty = bars + STAGES;        // [STAGES]  per CTA, multicast commit from the leader
