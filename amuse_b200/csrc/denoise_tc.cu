@@ -222,15 +222,23 @@ __device__ __forceinline__ void wait_bar_relaxed(const Ctx& k, uint64_t* bar, ui
 template <int UNITS, int QUADS>   // UNITS = my units in the tile, QUADS = feature quadrants stored
 __device__ __forceinline__ void produce_tile(const Ctx& k, const uint4* src, int q, int grp, uint32_t dst, uint64_t* empty_bar,
                                              uint32_t empty_parity, bool wait_empty) {
-  const int dbg = k.p->debug_flags;
   if (q >= QUADS) {   // the q|k|v tile has 96 features: nothing for the warps of the fourth quadrant
     if (wait_empty) wait_bar_relaxed(k, empty_bar, empty_parity);
     return;
   }
   constexpr int S = 2 * QUADS * 128 * 16;   // bytes between two of my units
   const uint4* s = src + (grp * QUADS + q) * 128;
+  // (the "no loads" / "no tcgen05.st" timing experiments of profiles/r02_sanitizer_summary.txt were runtime flags here;
+  //  their zero-initialised registers and predicated loads were 9 % of everything the SM issued, so they are now a
+  //  developer build: -DAMUSE_DN2_PRODUCER_DEBUG)
+#ifdef AMUSE_DN2_PRODUCER_DEBUG
+  const int dbg = k.p->debug_flags;
   uint4 a[4] = {}, b[4] = {}, c[4] = {}, d[4] = {};
-  if (!(dbg & 2)) {
+  if (!(dbg & 2))
+#else
+  uint4 a[4], b[4], c[4], d[4];
+#endif
+  {
 #define DN2_LOAD(R, J)                           \
   R[0] = ldg_stream<(J) * S>(s);                 \
   R[1] = ldg_stream<(J) * S + 512>(s);           \
@@ -243,10 +251,12 @@ __device__ __forceinline__ void produce_tile(const Ctx& k, const uint4* src, int
   }
   if (wait_empty) wait_bar_relaxed(k, empty_bar, empty_parity);   // the MMAs on the previous occupant are complete
   tc_fence_after();
+#ifdef AMUSE_DN2_PRODUCER_DEBUG
   if (dbg & 4) {   // timing experiment: loads only
     asm volatile("" ::"r"(a[0].x ^ a[3].w ^ b[0].x ^ b[3].w ^ c[0].x ^ c[3].w ^ d[0].x ^ d[3].w));
     return;
   }
+#endif
   tmem_st16(dst + grp * 16, a);
   if constexpr (UNITS > 1) tmem_st16(dst + (grp + 2) * 16, b);
   if constexpr (UNITS > 2) {
@@ -321,9 +331,10 @@ __device__ __forceinline__ void issue_tile(uint32_t a, uint32_t d, uint64_t bdes
     umma_f16_ts(d + 16, a + K / 2 + kk * 8, bd, kIdescN16, 1u);            // W_lo' . x_hi
   }
 }
+template <bool PROF>
 __device__ __forceinline__ void issuer_loop(const Ctx& k) {
   const Params& p = *k.p;
-  const bool prof_cta = (p.prof != nullptr) && cluster_id_x() == 0 && cluster_ctarank() == 0;
+  const bool prof_cta = PROF && (p.prof != nullptr) && cluster_id_x() == 0 && cluster_ctarank() == 0;
   const uint64_t dBx = umma_desc(smem_u32(k.smem + oBx)), dBo = umma_desc(smem_u32(k.smem + oBo)),
                  dBh = umma_desc(smem_u32(k.smem + oBh));
   uint32_t slot = 0, use = 0, suse = 0;
@@ -635,14 +646,17 @@ struct Chain {
     }
   }
 
+  template <bool PROF>
   __device__ void run();
 };
 
+// PROF = the kernel instantiation with the in-kernel clock stamps (amuse_profile_arm); the product launch compiles them out
+template <bool PROF>
 __device__ void Chain::run() {
   const Params& p = *k.p;
   const int T = p.T;
   const int clip = static_cast<int>(cluster_id_x());
-  const bool do_prof_chain = (p.prof != nullptr) && clip == 0 && rank == 0 && t == 0 && f == 0;
+  const bool do_prof_chain = PROF && (p.prof != nullptr) && clip == 0 && rank == 0 && t == 0 && f == 0;
   float* const SK = reinterpret_cast<float*>(smem + oSK);
   const int row0 = t * kNR, nr = t ? 2 : 3;   // my rows in the row-split epilogues
 
@@ -829,6 +843,7 @@ __device__ void Chain::run() {
 }  // namespace
 
 // ================================================================= the kernel
+template <bool PROF>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     denoise_tc_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -874,9 +889,9 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     producer_loop(k, warp, lane, rank);
   } else if (warp < kProdWarps + kChainWarps) {
     Chain ch(k, warp & 3, (warp - kProdWarps) >> 2, lane, rank);
-    ch.run();
+    ch.template run<PROF>();
   } else {
-    issuer_loop(k);
+    issuer_loop<PROF>(k);
   }
 
   tc_fence_before();
@@ -902,13 +917,16 @@ cudaError_t launch(const Params& p, cudaStream_t stream) {
       for (int i = 0; i < kTilesPerStep; ++i) tile_info(i, tab[i].x, tab[i].y);
       cudaError_t e = cudaMemcpyToSymbol(c_tiles, tab, sizeof(tab));
       if (e != cudaSuccess) return e;
-      e = cudaFuncSetAttribute(denoise_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+      e = cudaFuncSetAttribute(denoise_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(denoise_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
       if (e != cudaSuccess) return e;
       configured_dev[dev & 63] = true;
     }
   }
   if (p.B < 1 || p.T < 2 || p.T > kTMax || p.n_steps < 1) return cudaErrorInvalidValue;
-  denoise_tc_kernel<<<dim3(p.B * kCluster), dim3(kThreads), kSmemBytes, stream>>>(p);
+  if (p.prof) denoise_tc_kernel<true><<<dim3(p.B * kCluster), dim3(kThreads), kSmemBytes, stream>>>(p);
+  else denoise_tc_kernel<false><<<dim3(p.B * kCluster), dim3(kThreads), kSmemBytes, stream>>>(p);
   return cudaGetLastError();
 }
 

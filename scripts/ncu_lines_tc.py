@@ -27,7 +27,14 @@ subprocess.run(["cuobjdump", "-xelf", "denoise_tc", str(ROOT / "amuse_b200/lib/l
 cub = [c for c in glob.glob(tmp + "/*.cubin") if "denoise_tc.sm" in c or c.endswith("denoise_tc.sm_100a.cubin")] or glob.glob(tmp + "/*.cubin")
 dis = subprocess.run(["nvdisasm", "-g", "-c", cub[0]], capture_output=True, text=True).stdout.splitlines()
 line, amap = None, {}
+inside = True   # the cubin holds two instantiations of the kernel (PROF = false / true): map the product one
 for l in dis:
+    ms = re.match(r"\s*\.section\s+\.text\.(\S+?),", l)
+    if ms:
+        inside = "denoise_tc_kernelILb0E" in ms.group(1)
+        continue
+    if not inside:
+        continue
     m = re.search(r'//## File ".*?([^/"]+)", line (\d+)', l)
     if m:
         line = (m.group(1), int(m.group(2)))
