@@ -351,6 +351,11 @@ __device__ __forceinline__ void issuer_loop(const Ctx& k) {
         s2 = 0;
         ++u2;
       }
+      // profiled step: per stage, how long the weights kept the issuer (slots 300 + 2 stage) and how long it then waited
+      // for the B operand (301 + 2 stage): a stage whose second number is ~0 was held up by its weights
+      const bool wprof = prof_cta && step == p.prof_step;
+      long long t_in = 0, t_full = 0;
+      if (wprof) t_in = clock64();
       if (side) {
         wait_bar(k, k.sfull(0), suse & 1);
         wait_bar(k, k.sfull(1), suse & 1);
@@ -358,7 +363,12 @@ __device__ __forceinline__ void issuer_loop(const Ctx& k) {
         wait_bar(k, k.full(slot), use & 1);
         wait_bar(k, k.full(s2), u2 & 1);
       }
+      if (wprof) t_full = clock64();
       asm volatile("bar.sync 4, 288;" ::: "memory");   // "B operand ready": all 8 epilogue warps have arrived (signal_b)
+      if (wprof && elect_one()) {
+        p.prof[300 + 2 * stage] = t_full - t_in;
+        p.prof[301 + 2 * stage] = clock64() - t_full;
+      }
       tc_fence_after();
       const bool fine = prof_cta && step == p.prof_step && (stage == 5 || stage == 6);
       if (fine && elect_one()) p.prof[stage == 5 ? 108 : 112] = clock64();

@@ -60,6 +60,14 @@ def main():
             row.append(st[base + j] - (prev if j == 0 else st[base + j - 1]))
         print(f"layer {l}: " + " ".join(f"{n}={c}" for n, c in zip(names, row)))
     print("final+update:", st[92] - st[2 + 8 * 10 + 7])
+    if len(st) >= 400 and any(st[300:380]):   # issuer: cycles held by the weights | then waiting for the B operand, per stage
+        kinds = ["qkv", "wo", "w1", "w2"]
+        names = [f"L{i // 4}.{kinds[i % 4]}" for i in range(20)] + \
+                [f"L{5 + i // 5}.{(['sk'] + kinds)[i % 5]}" for i in range(20)]
+        late = [(names[i], st[300 + 2 * i], st[301 + 2 * i]) for i in range(40)]
+        print("issuer per stage (weights-wait | B-wait): " + "  ".join(f"{n}={a}|{b}" for n, a, b in late))
+        print("stages held up by their weights (B-wait < 60):", [n for n, a, b in late if b < 60],
+              " total weights-wait", sum(a for _, a, _ in late))
     if not st[128]:
         print("layer0 exchange waits: out_proj", st[5] - st[105], " ffn2", st[8] - st[108])
     if len(st) >= 512 and st[128]:   # tensor-core kernel: per-warp stamps inside the out_proj and FFN1 stages of layer 1
