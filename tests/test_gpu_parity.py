@@ -421,3 +421,19 @@ def test_attention_kernels_match(engine, synthetic_weights, monkeypatch):
         assert d < 2 * TOL_FEATS
     finally:
         ffma.close()
+
+
+def test_profiling_instantiation_matches_product(engine):
+    """`amuse_profile_arm` launches the second instantiation of the sampler loop (denoise_tc_kernel<true>, with the in-kernel
+    clock stamps); the product launch compiles them out.  Same latents bit for bit, and the stamps are filled."""
+    g = torch.Generator().manual_seed(21)
+    l0, con, emo, sty = (torch.randn(6, d, generator=g) for d in (128, 256, 256, 256))
+    ref = engine.denoise(l0, con, emo, sty, n_steps=6, sampler="ddpm", seed=5).cpu()
+    engine.profile_arm(2)
+    got = engine.denoise(l0, con, emo, sty, n_steps=6, sampler="ddpm", seed=5).cpu()
+    st = engine.profile_read(512)
+    assert torch.equal(got, ref)
+    if os.environ.get("AMUSE_DENOISE_FFMA") != "1":
+        assert st[92] > st[0] > 0 and 20_000 < st[92] - st[0] < 2_000_000     # one denoiser step, in cycles
+        assert all(v > 0 for v in st[300:380])                                 # the issuer's per-stage stamps
+    assert torch.equal(engine.denoise(l0, con, emo, sty, n_steps=6, sampler="ddpm", seed=5).cpu(), ref)   # disarmed again
