@@ -603,6 +603,14 @@ struct Chain {
     const bool at_pv = at_live && at_l < 8;
     const float4* qv = reinterpret_cast<const float4*>(QKVs + at_row * kQkvLd + 16 * at_c);
     const float4* kv = reinterpret_cast<const float4*>(QKVs + at_j * kQkvLd + 32 + 16 * at_c);
+    // the value rows do not depend on the scores: fetched up front, under the score chain (8 lanes per row: 4 head
+    // dimensions each)
+    float4 v4[5];
+    {
+      const float* vb = QKVs + 64 + 4 * (at_l & 7);
+#pragma unroll
+      for (int jj = 0; jj < 5; ++jj) v4[jj] = *reinterpret_cast<const float4*>(vb + ((jj < T) ? jj : 0) * kQkvLd);
+    }
     float p0, p1, p2, p3;
     {
       const float4 a = qv[0], b = kv[0];
@@ -632,19 +640,17 @@ struct Chain {
 #pragma unroll
     for (int jj = 0; jj < 5; ++jj) ej[jj] = __shfl_sync(0xffffffffu, e, at_src + 2 * jj);
     const float sum = ((ej[0] + ej[1]) + (ej[2] + ej[3])) + ej[4];
+    const float inv = __frcp_rn(sum);
     if (at_pv) {   // 8 lanes per row: 4 head dimensions each
-      const float* vb = QKVs + 64 + 4 * at_l;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int jj = 0; jj < 5; ++jj)
         if (jj < T) {
-          const float4 v4 = *reinterpret_cast<const float4*>(vb + jj * kQkvLd);
-          acc.x = fmaf(ej[jj], v4.x, acc.x);
-          acc.y = fmaf(ej[jj], v4.y, acc.y);
-          acc.z = fmaf(ej[jj], v4.z, acc.z);
-          acc.w = fmaf(ej[jj], v4.w, acc.w);
+          acc.x = fmaf(ej[jj], v4[jj].x, acc.x);
+          acc.y = fmaf(ej[jj], v4[jj].y, acc.y);
+          acc.z = fmaf(ej[jj], v4[jj].z, acc.z);
+          acc.w = fmaf(ej[jj], v4[jj].w, acc.w);
         }
-      const float inv = __frcp_rn(sum);
       const float o[4] = {acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv};
       uint16_t h[4], l[4];
 #pragma unroll
