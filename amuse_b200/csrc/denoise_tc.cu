@@ -94,6 +94,11 @@ constexpr uint32_t kXchgBytes = kPsSlot;          // what one exchange delivers:
 __constant__ int2 c_tiles[kTilesPerStep];   // (kind, offset in uint4) of tile i
 
 // ---- small PTX helpers
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void bar_named(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void umma_f16_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -635,10 +640,11 @@ struct Chain {
     float m = sj[0];
 #pragma unroll
     for (int jj = 1; jj < 5; ++jj) m = (jj < T) ? fmaxf(m, sj[jj]) : m;
-    const float e = at_key ? expf(sc - m) : 0.f;
+    // every lane of the row exponentiates the 5 scores itself (q carries log2 e, so exp is one ex2.approx): a second
+    // gather of 5 shuffles would sit on the dependency chain
     float ej[5];
 #pragma unroll
-    for (int jj = 0; jj < 5; ++jj) ej[jj] = __shfl_sync(0xffffffffu, e, at_src + 2 * jj);
+    for (int jj = 0; jj < 5; ++jj) ej[jj] = (jj < T) ? ex2_approx(sj[jj] - m) : 0.f;
     const float sum = ((ej[0] + ej[1]) + (ej[2] + ej[3])) + ej[4];
     const float inv = __frcp_rn(sum);
     if (at_pv) {   // 8 lanes per row: 4 head dimensions each
@@ -742,7 +748,7 @@ __device__ void Chain::run() {
       {
         float y[kNR];
         const float b0 = __ldg(vec(0)), b1 = __ldg(vec(1));
-        const float sc = (q == 0) ? 0.17677669529663687f : 1.0f;
+        const float sc = (q == 0) ? 0.17677669529663687f * 1.4426950408889634f : 1.0f;   // head_dim^-0.5, and log2 e for the softmax
         float* const Q0 = reinterpret_cast<float*>(smem + oQKV) + row0 * kQkvLd + f;
         signal_b();
         // the noise draw does not depend on the chain: off the critical path, while the first MMAs of the step run
