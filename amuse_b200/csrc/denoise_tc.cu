@@ -426,6 +426,7 @@ struct Chain {
   const uint32_t rank;
   uint8_t* const smem;
   const uint32_t lane_taddr;  // TMEM address of my lane, column 0
+  const uint32_t peer_ps, peer_ps2, peer_xbar;   // shared::cluster addresses in the peer CTA: my receive-slot entries (buffer 0), its xbar(0)
   uint32_t g_tile = 0;        // stage in the step
   uint32_t dph0 = 0, dph1 = 0, xe = 0;
   long long* wprof = nullptr; // debug: this warp's stamp row (lane 0 of every epilogue warp of cluster 0 / CTA 0), armed for
@@ -438,7 +439,10 @@ struct Chain {
 
   __device__ Chain(const Ctx& k_, int q_, int t_, int lane_, uint32_t rank_)
       : k(k_), q(q_), t(t_), lane(lane_), f(q_ * 32 + lane_), rank(rank_), smem(k_.smem),
-        lane_taddr(k_.tmem + (static_cast<uint32_t>(q_ * 32) << 16)) {}
+        lane_taddr(k_.tmem + (static_cast<uint32_t>(q_ * 32) << 16)),
+        peer_ps(map_to_rank(k_.smem + oPs, rank_ ^ 1u) + t_ * 1024 + (q_ * 32 + lane_) * 8),
+        peer_ps2(map_to_rank(k_.smem + oPs, rank_ ^ 1u) + 2048 + (q_ * 32 + lane_) * 4),
+        peer_xbar(map_to_rank(k_.xbar(0), rank_ ^ 1u)) {}
 
   __device__ __forceinline__ void bar_group() const { bar_named(2 + t); }
   __device__ __forceinline__ void bar_all() const { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -510,15 +514,9 @@ struct Chain {
     if (f == 0 && t == 0) mbar_arrive_expect_tx(k.xbar(xe & 1), kXchgBytes);
   }
   __device__ __forceinline__ void xchg_send(const float (&y)[kNR]) const {
-    uint8_t* ps = smem + oPs + (xe & 1) * kPsSlot;
-    const uint32_t peer = rank ^ 1u;
-    const uint32_t rb = map_to_rank(k.xbar(xe & 1), peer);
-    if (t == 0) {
-      st_async_v2(map_to_rank(ps + f * 8, peer), y[0], y[1], rb);
-      st_async_b32(map_to_rank(ps + 2048 + f * 4, peer), y[2], rb);
-    } else {
-      st_async_v2(map_to_rank(ps + 1024 + f * 8, peer), y[0], y[1], rb);
-    }
+    const uint32_t b = xe & 1u, off = b * kPsSlot, rb = peer_xbar + b * 8u;   // peer addresses: mapped once (constructor)
+    st_async_v2(peer_ps + off, y[0], y[1], rb);
+    if (t == 0) st_async_b32(peer_ps2 + off, y[2], rb);
   }
   __device__ __forceinline__ void xchg_recv(float (&v)[kNR]) {
     wait_group(k.xbar(xe & 1), (xe >> 1) & 1);
