@@ -336,75 +336,85 @@ __device__ __forceinline__ void issue_tile(uint32_t a, uint32_t d, uint64_t bdes
     umma_f16_ts(d + 16, a + K / 2 + kk * 8, bd, kIdescN16, 1u);            // W_lo' . x_hi
   }
 }
+// One stage of the issuer, specialised on the tile kind: everything but the ring position is a compile-time constant,
+// so the path from the "B operand ready" barrier to the first tcgen05.mma is a handful of uniform-datapath instructions
+// (with the kind looked up per stage at run time it was ~25, on the critical path of all 41 stages).
+struct IssuerState {
+  uint32_t slot = 0, use = 0, suse = 0;
+};
+template <int KIND, bool PROF>
+__device__ __forceinline__ void issue_stage(const Ctx& k, IssuerState& st, uint64_t bdesc, int step, int stage, bool prof_cta) {
+  const Params& p = *k.p;
+  constexpr bool nsplit = (KIND == kQKV) || (KIND == kW1);
+  constexpr bool side = (KIND == kWO);
+  constexpr int ksteps = (KIND == kWO) ? 2 : (KIND == kSK) ? 4 : 8;
+  constexpr int K = tile_K(KIND);
+  // the stage's two weight tiles (usually long in TMEM): observed here, while the epilogue warps are still busy
+  uint32_t s2 = st.slot + 1, u2 = st.use;
+  if (s2 == kSlots) {
+    s2 = 0;
+    ++u2;
+  }
+  const uint32_t a0 = k.tmem + (side ? kColSide : st.slot * kSlotCols), a1 = k.tmem + (side ? kColSide + 32 : s2 * kSlotCols);
+  const uint32_t d0 = k.tmem + kColD, d1 = k.tmem + kColD + (nsplit ? 32 : 0);
+  // profiled step: per stage, how long the weights kept the issuer (slots 300 + 2 stage) and how long it then waited
+  // for the B operand (301 + 2 stage): a stage whose second number is ~0 was held up by its weights
+  const bool wprof = PROF && prof_cta && step == p.prof_step;
+  long long t_in = 0, t_full = 0;
+  if (wprof) t_in = clock64();
+  if (side) {
+    wait_bar(k, k.sfull(0), st.suse & 1);
+    wait_bar(k, k.sfull(1), st.suse & 1);
+  } else {
+    wait_bar(k, k.full(st.slot), st.use & 1);
+    wait_bar(k, k.full(s2), u2 & 1);
+  }
+  if (wprof) t_full = clock64();
+  asm volatile("bar.sync 4, 288;" ::: "memory");   // "B operand ready": all 8 epilogue warps have arrived (signal_b)
+  if (wprof && elect_one()) {
+    p.prof[300 + 2 * stage] = t_full - t_in;
+    p.prof[301 + 2 * stage] = clock64() - t_full;
+  }
+  tc_fence_after();
+  const bool fine = PROF && prof_cta && step == p.prof_step && (stage == 5 || stage == 6);
+  if (fine && elect_one()) p.prof[stage == 5 ? 108 : 112] = clock64();
+  if (elect_one()) {
+    issue_tile<K>(a0, d0, bdesc, 0, false);
+    if (nsplit) umma_commit(k.dbar(0));
+    umma_commit(side ? k.sempty(0) : k.empty(st.slot));
+    issue_tile<K>(a1, d1, bdesc, nsplit ? 0 : ksteps, !nsplit);
+    umma_commit(nsplit ? k.dbar(1) : k.dbar(0));
+    umma_commit(side ? k.sempty(1) : k.empty(s2));
+  }
+  __syncwarp();
+  if (fine && elect_one()) p.prof[stage == 5 ? 109 : 113] = clock64();
+  if (side) {
+    ++st.suse;
+  } else {
+    st.slot = s2 + 1;
+    st.use = u2;
+    if (st.slot == kSlots) {
+      st.slot = 0;
+      ++st.use;
+    }
+  }
+}
 template <bool PROF>
 __device__ __forceinline__ void issuer_loop(const Ctx& k) {
   const Params& p = *k.p;
   const bool prof_cta = PROF && (p.prof != nullptr) && cluster_id_x() == 0 && cluster_ctarank() == 0;
   const uint64_t dBx = umma_desc(smem_u32(k.smem + oBx)), dBo = umma_desc(smem_u32(k.smem + oBo)),
                  dBh = umma_desc(smem_u32(k.smem + oBh));
-  uint32_t slot = 0, use = 0, suse = 0;
+  IssuerState st;
   for (int step = 0; step < p.n_steps; ++step) {
-    for (int stage = 0; stage < kTilesPerStep; ++stage) {
-      const int kind = c_tiles[stage].x;
-      const bool nsplit = (kind == kQKV) || (kind == kW1);
-      const uint64_t bdesc = (kind == kWO) ? dBo : (kind == kW2) ? dBh : dBx;
-      const int ksteps = (kind == kWO) ? 2 : (kind == kSK) ? 4 : 8;
-      // the stage's two weight tiles (usually long in TMEM): observed here, while the epilogue warps are still busy
-      const bool side = (kind == kWO);
-      uint32_t s2 = slot + 1, u2 = use;
-      if (s2 == kSlots) {
-        s2 = 0;
-        ++u2;
-      }
-      // profiled step: per stage, how long the weights kept the issuer (slots 300 + 2 stage) and how long it then waited
-      // for the B operand (301 + 2 stage): a stage whose second number is ~0 was held up by its weights
-      const bool wprof = prof_cta && step == p.prof_step;
-      long long t_in = 0, t_full = 0;
-      if (wprof) t_in = clock64();
-      if (side) {
-        wait_bar(k, k.sfull(0), suse & 1);
-        wait_bar(k, k.sfull(1), suse & 1);
-      } else {
-        wait_bar(k, k.full(slot), use & 1);
-        wait_bar(k, k.full(s2), u2 & 1);
-      }
-      if (wprof) t_full = clock64();
-      asm volatile("bar.sync 4, 288;" ::: "memory");   // "B operand ready": all 8 epilogue warps have arrived (signal_b)
-      if (wprof && elect_one()) {
-        p.prof[300 + 2 * stage] = t_full - t_in;
-        p.prof[301 + 2 * stage] = clock64() - t_full;
-      }
-      tc_fence_after();
-      const bool fine = prof_cta && step == p.prof_step && (stage == 5 || stage == 6);
-      if (fine && elect_one()) p.prof[stage == 5 ? 108 : 112] = clock64();
-      if (elect_one()) {
-#pragma unroll
-        for (int t = 0; t < kVirt; ++t) {
-          const uint32_t sl = t ? s2 : slot;
-          const uint32_t a = k.tmem + (side ? kColSide + t * 32 : sl * kSlotCols);
-          const uint32_t d = k.tmem + kColD + (nsplit ? t * 32 : 0);
-          const int jbase = nsplit ? 0 : t * ksteps;
-          const bool acc0 = !nsplit && t > 0;
-          if (kind == kWO) issue_tile<32>(a, d, bdesc, jbase, acc0);
-          else if (kind == kSK) issue_tile<64>(a, d, bdesc, jbase, acc0);
-          else issue_tile<128>(a, d, bdesc, jbase, acc0);
-          if (nsplit) umma_commit(k.dbar(t));
-          else if (t == kVirt - 1) umma_commit(k.dbar(0));
-          umma_commit(side ? k.sempty(t) : k.empty(sl));
-        }
-      }
-      __syncwarp();
-      if (fine && elect_one()) p.prof[stage == 5 ? 109 : 113] = clock64();
-      if (side) {
-        ++suse;
-      } else {
-        slot = s2 + 1;
-        use = u2;
-        if (slot == kSlots) {
-          slot = 0;
-          ++use;
-        }
-      }
+    int stage = 0;   // the stage order of a step: layers 0..4 qkv|wo|w1|w2, layers 5..8 sk|qkv|wo|w1|w2 (tile_info)
+#pragma unroll 1
+    for (int layer = 0; layer < kLayers; ++layer) {
+      if (layer >= 5) issue_stage<kSK, PROF>(k, st, dBx, step, stage++, prof_cta);
+      issue_stage<kQKV, PROF>(k, st, dBx, step, stage++, prof_cta);
+      issue_stage<kWO, PROF>(k, st, dBo, step, stage++, prof_cta);
+      issue_stage<kW1, PROF>(k, st, dBx, step, stage++, prof_cta);
+      issue_stage<kW2, PROF>(k, st, dBh, step, stage++, prof_cta);
     }
   }
 }
