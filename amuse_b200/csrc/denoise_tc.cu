@@ -91,7 +91,6 @@ static_assert(oBo % 1024 == 0 && oBh % 1024 == 0, "B operands must be 1024-B ali
 static_assert(kSmemUsed + 1024 <= kSmemBytes, "shared-memory carve-up");
 constexpr uint32_t kXchgBytes = kPsSlot;          // what one exchange delivers: the peer's 128 features x 5 rows
 
-__constant__ int2 c_tiles[kTilesPerStep];   // (kind, offset in uint4) of tile i
 
 // ---- small PTX helpers
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -269,58 +268,66 @@ __device__ __forceinline__ void produce_tile(const Ctx& k, const uint4* src, int
     tmem_st16(dst + (grp + 6) * 16, d);
   }
 }
+struct ProducerState {
+  const uint4* src;             // my lane's position in the CTA's weight stream
+  uint32_t slot = 0, use = 0;   // ring slot and use count of the next ring tile
+  uint32_t suse = 0;            // use count of the side slots
+};
+// the two tiles (ranks 2r, 2r + 1) of one stage, specialised on the tile kind like the issuer's stages
+template <int KIND>
+__device__ __forceinline__ void produce_stage(const Ctx& k, ProducerState& st, int q, int grp, int lane, uint32_t lane_base,
+                                              bool off) {
+  constexpr int UNITS = (KIND == kWO) ? 1 : (KIND == kSK) ? 2 : 4;   // my units of the tile
+  constexpr int QUADS = (KIND == kQKV) ? 3 : 4;
+#pragma unroll
+  for (int t = 0; t < kVirt; ++t) {
+    if (KIND == kWO) {
+      if (off) {
+        if (st.suse > 0) wait_bar_relaxed(k, k.sempty(t), (st.suse - 1) & 1);
+      } else {
+        produce_tile<UNITS, QUADS>(k, st.src, q, grp, lane_base + kColSide + t * 32, k.sempty(t), (st.suse - 1) & 1,
+                                   st.suse > 0);
+      }
+    } else {
+      const bool we = st.use > 0;
+      const uint32_t par = (st.use - 1) & 1;
+      if (off) {
+        if (we) wait_bar_relaxed(k, k.empty(st.slot), par);
+      } else {
+        produce_tile<UNITS, QUADS>(k, st.src, q, grp, lane_base + st.slot * kSlotCols, k.empty(st.slot), par, we);
+      }
+    }
+    st.src += tile_vec4(KIND);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (KIND == kWO) {
+      if (lane == 0) mbar_arrive(k.sfull(t));
+    } else {
+      if (lane == 0) mbar_arrive(k.full(st.slot));
+      if (++st.slot == kSlots) {
+        st.slot = 0;
+        ++st.use;
+      }
+    }
+  }
+  if (KIND == kWO) ++st.suse;
+}
 __device__ __forceinline__ void producer_loop(const Ctx& k, int pw, int lane, uint32_t rank) {
   const int q = pw & 3, grp = pw >> 2;
   const uint32_t lane_base = k.tmem + (static_cast<uint32_t>(q * 32) << 16);
   const uint4* const src0 = k.p->blob + static_cast<size_t>(rank) * (kVirt * kRankVec4) + lane;
   const bool off = (k.p->debug_flags & 1) != 0;
-  uint32_t slot = 0, use = 0;   // ring slot and use count of the next ring tile
-  uint32_t suse = 0;            // use count of the side slots
+  ProducerState st;
   for (int step = 0; step < k.p->n_steps; ++step) {
-    const uint4* src = src0;
-    for (int stage = 0; stage < kTilesPerStep; ++stage) {
-      const int kind = c_tiles[stage].x;
-      if (kind == kWO) {
-#pragma unroll
-        for (int t = 0; t < kVirt; ++t) {
-          if (off) {
-            if (suse > 0) wait_bar_relaxed(k, k.sempty(t), (suse - 1) & 1);
-          } else {
-            produce_tile<1, 4>(k, src, q, grp, lane_base + kColSide + t * 32, k.sempty(t), (suse - 1) & 1, suse > 0);
-          }
-          src += tile_vec4(kWO);
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(k.sfull(t));
-        }
-        ++suse;
-        continue;
-      }
-#pragma unroll
-      for (int t = 0; t < kVirt; ++t) {
-        const uint32_t dst = lane_base + slot * kSlotCols;
-        const bool we = use > 0;
-        const uint32_t par = (use - 1) & 1;
-        if (off) {
-          if (we) wait_bar_relaxed(k, k.empty(slot), par);
-        } else if (kind == kQKV) {
-          produce_tile<4, 3>(k, src, q, grp, dst, k.empty(slot), par, we);
-        } else if (kind == kSK) {
-          produce_tile<2, 4>(k, src, q, grp, dst, k.empty(slot), par, we);
-        } else {
-          produce_tile<4, 4>(k, src, q, grp, dst, k.empty(slot), par, we);
-        }
-        src += (kind == kQKV) ? tile_vec4(kQKV) : (kind == kSK) ? tile_vec4(kSK) : tile_vec4(kW1);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(k.full(slot));
-        if (++slot == kSlots) {
-          slot = 0;
-          ++use;
-        }
-      }
+    st.src = src0;
+#pragma unroll 1
+    for (int layer = 0; layer < kLayers; ++layer) {   // the stream order of tile_info(): layers 5..8 start with the skip tile
+      if (layer >= 5) produce_stage<kSK>(k, st, q, grp, lane, lane_base, off);
+      produce_stage<kQKV>(k, st, q, grp, lane, lane_base, off);
+      produce_stage<kWO>(k, st, q, grp, lane, lane_base, off);
+      produce_stage<kW1>(k, st, q, grp, lane, lane_base, off);
+      produce_stage<kW2>(k, st, q, grp, lane, lane_base, off);
     }
   }
 }
@@ -937,17 +944,13 @@ size_t smem_bytes() { return static_cast<size_t>(kSmemBytes); }
 
 cudaError_t launch(const Params& p, cudaStream_t stream) {
   static std::mutex mu;
-  static bool configured_dev[64] = {};   // attributes and __constant__ data are per device
+  static bool configured_dev[64] = {};   // function attributes are per device
   int dev = 0;
   cudaGetDevice(&dev);
   {
     std::lock_guard<std::mutex> lock(mu);
     if (!configured_dev[dev & 63]) {
-      int2 tab[kTilesPerStep];
-      for (int i = 0; i < kTilesPerStep; ++i) tile_info(i, tab[i].x, tab[i].y);
-      cudaError_t e = cudaMemcpyToSymbol(c_tiles, tab, sizeof(tab));
-      if (e != cudaSuccess) return e;
-      e = cudaFuncSetAttribute(denoise_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+      cudaError_t e = cudaFuncSetAttribute(denoise_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
       if (e != cudaSuccess) return e;
       e = cudaFuncSetAttribute(denoise_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
       if (e != cudaSuccess) return e;
