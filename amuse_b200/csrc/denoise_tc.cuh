@@ -74,7 +74,8 @@ struct Params {
   unsigned long long seed_elem_base;   // global index of this launch's first latent element (multi-GPU shards)
   int prof_step;
   int prune_last;            // last layer evaluated for token 0 only (same result)
-  int debug_flags;           // timing experiments only (results are garbage): 1 = producers idle, 2 = no global loads, 4 = no tcgen05.st
+  int debug_flags;           // timing experiments only (results are garbage): 1 = producers idle (AMUSE_DN2_DEBUG=1);
+                             // 2 = no global loads, 4 = no tcgen05.st only in a -DAMUSE_DN2_PRODUCER_DEBUG build
 };
 
 size_t smem_bytes();
